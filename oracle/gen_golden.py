@@ -1,0 +1,163 @@
+"""
+Golden-vector generator: runs the REAL reference (GPry 3.0.0 imported from /root/reference
+through ``oracle/ref_import.py``) and writes small ``tests/golden/*.npz`` fixtures.
+
+Run in the build container only (``python oracle/gen_golden.py``); the fixtures are committed
+and travel to the GPU box, the reference does not.  Each fixture stores the inputs needed to
+rebuild the case (or the seed that regenerates them with ``numpy.random.default_rng``) and
+the reference's outputs at the drop-in boundary:
+
+  predict(return_std)            gpr.py:1022-1273      -> mean, std
+  predict(return_mean_grad, ..)  gpr.py:1236-1266      -> grad_mean, grad_std (1 point)
+  predict_std                    gpr.py:1275-1352
+  LogExp.f / LogExp.__call__     acquisition_functions.py:936-1009,1068-1074
+  log_marginal_likelihood        gpr.py:876-881 -> sklearn _gpr.py:541-656   (value, gradient)
+  L_, V_, alpha_                 gpr.py:1453-1465      (checksums + a few rows)
+  RankedPool.add                 gp_acquisition.py:1290-1670 (final pool indices, X, y, acq)
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle.ref_import import import_reference  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def target(X):
+    return -0.5 * np.sum(((X - 0.5) / 0.15) ** 2, axis=1)
+
+
+def make_reference_gpr(gpry, kind, X, y, theta, bounds, noise_level=1e-2, normalize=True,
+                       clip_factor=1.1):
+    """Fixed-theta reference GPR."""
+    from sklearn.base import clone
+    from gpry.preprocessing import Normalize_bounds, Normalize_y
+    kernel = {"rbf": "RBF", "matern15": {"Matern": {"nu": 1.5}},
+              "matern25": {"Matern": {"nu": 2.5}}}[kind]
+    gpr = gpry.gpr.GaussianProcessRegressor(
+        kernel=kernel, bounds=bounds, noise_level=noise_level, clip_factor=clip_factor,
+        preprocessing_X=Normalize_bounds(bounds) if normalize else None,
+        preprocessing_y=Normalize_y() if normalize else None,
+        account_for_inf=None, verbose=0)
+    gpr.kernel_ = clone(gpr.kernel)
+    gpr.kernel_.theta = np.asarray(theta)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gpr.append_to_data(X, y, fit_gpr=False)
+    return gpr
+
+
+def case(gpry, name, kind, N, d, M, seed, ell, c=1.0, bounds=None, normalize=True,
+         with_lml=True, pool=None, noise_level=1e-2, store_train=True):
+    rng = np.random.default_rng(seed)
+    if bounds is None:
+        bounds = np.array([[0.0, 1.0]] * d)
+    lo, hi = bounds[:, 0], bounds[:, 1]
+    U = rng.uniform(size=(N, d))
+    X = lo + U * (hi - lo)
+    y = target(U)
+    Xc = lo + rng.uniform(size=(M, d)) * (hi - lo)
+    theta = np.log(np.concatenate([[c], np.full(d, ell) * (1 + 0.1 * np.arange(d) / d)]))
+    gpr = make_reference_gpr(gpry, kind, X, y, theta, bounds, noise_level, normalize)
+    mean, std = gpr.predict(Xc, return_std=True, validate=False)
+    std_only = gpr.predict_std(Xc, validate=False)
+    mean_only = gpr.predict(Xc, validate=False)
+    zeta = d ** (-0.85)
+    LogExp = gpry.acquisition_functions.LogExp
+    with np.errstate(divide="ignore"):
+        acq_f = LogExp.f(mean, std, gpr.y_max, gpr.noise_level, zeta)
+    acq_call = LogExp(zeta=zeta)(Xc, gpr)
+    m1, s1, gm, gs = gpr.predict(Xc[:1], return_std=True, return_mean_grad=True,
+                                 return_std_grad=True, validate=False)
+    out = dict(
+        kind=kind, N=N, d=d, M=M, seed=seed, theta=theta, bounds=bounds,
+        noise_level=noise_level, normalize=normalize, zeta=zeta,
+        Xc=Xc, mean=mean, std=std, std_only=std_only, mean_only=mean_only,
+        acq_f=acq_f, acq_call=acq_call, grad_mean=gm, grad_std=gs,
+        y_mean=getattr(gpr.preprocessing_y, "mean_", 0.0),
+        y_std=getattr(gpr.preprocessing_y, "std_", 1.0),
+        y_max=gpr.y_max, alpha_=gpr.alpha_, V_rows=gpr.V_[[0, N // 2, N - 1]],
+        L_diag=np.diag(gpr.L_), V_fro=np.linalg.norm(gpr.V_),
+        condK=np.linalg.cond(gpr.L_) ** 2,
+    )
+    if store_train:
+        out.update(X_train=X, y_train=y)
+    if with_lml:
+        thetas = [theta, theta + 0.3 * rng.standard_normal(theta.shape)]
+        lml, grad = [], []
+        for th in thetas:
+            v, g = gpr.log_marginal_likelihood(th, eval_gradient=True, clone_kernel=True)
+            lml.append(v), grad.append(g)
+        out.update(lml_thetas=np.array(thetas), lml=np.array(lml), lml_grad=np.array(grad))
+    if pool is not None:
+        from functools import partial
+        Mp, n_points = pool
+        Xp = lo + np.random.default_rng(seed + 1).uniform(size=(Mp, d)) * (hi - lo)
+        yp, sp = gpr.predict(Xp, return_std=True, validate=False)
+        acq_func = partial(LogExp.f, baseline=gpr.y_max, noise_level=gpr.noise_level,
+                           zeta=zeta)
+        with np.errstate(divide="ignore"):
+            ap = acq_func(yp, sp)
+            for method in ("single sort acq", "bulk"):
+                rp = gpry.gp_acquisition.RankedPool(n_points, gpr=gpr, acq_func=acq_func,
+                                                    verbose=0)
+                rp.add(Xp, yp, sp, ap, method=method)
+                rp = rp.copy(drop_empty=True)
+                Xsel = rp.X[:n_points]
+                idx = np.array([int(np.flatnonzero(np.all(Xp == x, axis=1))[0])
+                                for x in Xsel])
+                tag = method.replace(" ", "_")
+                out[f"pool_idx_{tag}"] = idx
+                out[f"pool_y_{tag}"] = rp.y[:n_points]
+                out[f"pool_sigma_{tag}"] = rp.sigma[:n_points]
+                out[f"pool_acq_cond_{tag}"] = rp.acq_cond[:n_points]
+        out.update(pool_M=Mp, pool_n_points=n_points, pool_seed=seed + 1,
+                   pool_acq_top=np.sort(ap)[::-1][:64],
+                   pool_argsort_top=np.argsort(ap)[::-1][:64])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: N={N} d={d} M={M} kind={kind} cond(K)={out['condK']:.3g} "
+          f"std range [{std.min():.3g},{std.max():.3g}] finite acq "
+          f"{np.isfinite(acq_f).mean():.3f}")
+
+
+def nonpd_case(gpry):
+    """LML with a non-PD kernel matrix must return (-inf, 0)  (sklearn:_gpr.py:590-593)."""
+    rng = np.random.default_rng(5)
+    d, N = 2, 40
+    X = rng.uniform(size=(N, d))
+    X[1] = X[0]  # duplicate point, zero noise -> singular
+    y = target(X)
+    theta = np.log([1.0, 5.0, 5.0])
+    bounds = np.array([[0.0, 1.0]] * d)
+    gpr = make_reference_gpr(gpry, "rbf", X[2:], y[2:], theta, bounds, noise_level=1e-2)
+    gpr.X_train_ = X.copy()
+    gpr.y_train_ = (y - y.mean()) / y.std()
+    gpr.alpha = np.zeros(N)
+    v, g = gpr.log_marginal_likelihood(theta, eval_gradient=True, clone_kernel=True)
+    np.savez_compressed(os.path.join(OUT, "lml_nonpd.npz"), X_train_=gpr.X_train_,
+                        y_train_=gpr.y_train_, noise2=gpr.alpha, theta=theta, lml=v, grad=g)
+    print("lml_nonpd:", v, g)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    gpry = import_reference()
+    case(gpry, "rbf_d2_n60", "rbf", 60, 2, 128, 11, 0.3, pool=(4000, 4))
+    case(gpry, "rbf_d8_n300", "rbf", 300, 8, 256, 12, 0.5, pool=(20000, 8))
+    case(gpry, "matern25_d8_n300", "matern25", 300, 8, 256, 13, 0.8)
+    case(gpry, "matern15_d5_n200", "matern15", 200, 5, 256, 14, 0.7,
+         bounds=np.array([[-2.0, 3.0], [0.0, 10.0], [1.0, 1.5], [-5.0, -1.0], [0.0, 1.0]]))
+    case(gpry, "rbf_d12_n500_c4", "rbf", 500, 12, 256, 15, 1.0, c=4.0)
+    case(gpry, "rbf_d3_n100_raw", "rbf", 100, 3, 128, 16, 0.4, normalize=False)
+    case(gpry, "rbf_d8_n1000", "rbf", 1000, 8, 512, 1234, 0.5, with_lml=False,
+         store_train=False)
+    nonpd_case(gpry)
+
+
+if __name__ == "__main__":
+    main()
