@@ -1,0 +1,338 @@
+// extern "C" surface of libgpry_b200.so (see include/gpry_b200.h for the contract).
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "state.cuh"
+
+namespace gpry {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+TimedScope::TimedScope(gpry_state* st_, cudaStream_t s_, int cat_, int launches)
+    : st(st_), s(s_), cat(cat_) {
+  st->n_launches += launches;
+  if (!st->profiling) return;
+  auto get = [&]() {
+    cudaEvent_t e;
+    if (!st->pool.empty()) {
+      e = st->pool.back();
+      st->pool.pop_back();
+    } else {
+      GPRY_CUDA(cudaEventCreate(&e));
+    }
+    return e;
+  };
+  e0 = get();
+  e1 = get();
+  cudaEventRecord(e0, s);
+}
+TimedScope::~TimedScope() {
+  if (!e0) return;
+  cudaEventRecord(e1, s);
+  st->pending.push_back(EventPair{cat, e0, e1});
+}
+void resolve_timings(gpry_state* st) {
+  for (auto& p : st->pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.e1) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess)
+      st->t_ms[p.cat] += ms;
+    st->pool.push_back(p.e0);
+    st->pool.push_back(p.e1);
+  }
+  st->pending.clear();
+}
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return GPRY_OK;
+  } catch (const GpryError& e) {
+    set_last_error(e.msg);
+    cudaGetLastError();
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error(std::string("exception: ") + e.what());
+    return GPRY_ERR_ARG;
+  }
+}
+
+// stage a host input on the device (or pass a device pointer through)
+static const double* stage_in(gpry_state* st, const double* X, size_t n, bool on_device,
+                              DevBuf<double>& buf, cudaStream_t s) {
+  if (on_device) return X;
+  buf.reserve(n);
+  TimedScope ts(st, s, T_H2D, 0);
+  GPRY_CUDA(cudaMemcpyAsync(buf.p, X, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  return buf.p;
+}
+
+}  // namespace gpry
+
+using namespace gpry;
+
+extern "C" {
+
+int gpry_abi_version(void) { return GPRY_ABI_VERSION; }
+const char* gpry_last_error(void) { return g_last_error.c_str(); }
+
+int gpry_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return n;
+}
+
+int gpry_state_create(int device, gpry_state** out) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(out != nullptr, "out is NULL");
+    int n = 0;
+    GPRY_CUDA(cudaGetDeviceCount(&n));
+    GPRY_CHECK_ARG(device >= 0 && device < n, "no such CUDA device");
+    GPRY_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    GPRY_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10)
+      throw GpryError{GPRY_ERR_ARG, std::string("gpry_b200 is built for sm_100a only; device is ") +
+                                        p.name};
+    gpry_state* st = new gpry_state();
+    st->device = device;
+    st->n_sm = p.multiProcessorCount;
+    *out = st;
+  });
+}
+
+int gpry_state_destroy(gpry_state* st) {
+  return guarded([&] {
+    if (!st) return;
+    cudaSetDevice(st->device);
+    resolve_timings(st);
+    for (auto e : st->pool) cudaEventDestroy(e);
+    st->prm_dev.release(); st->T.release(); st->Xt.release(); st->alpha.release();
+    st->Vt.release(); st->Ks.release(); st->meanp.release(); st->ssqp.release();
+    st->Xdev.release(); st->o_mean.release(); st->o_std.release(); st->o_acq.release();
+    for (int b = 0; b < 2; b++) { st->tk_keys[b].release(); st->tk_idx[b].release(); }
+    st->tmp.release(); st->small.release();
+    st->f_K.release(); st->f_VT.release(); st->f_W.release(); st->f_vec.release();
+    delete st;
+  });
+}
+
+int gpry_state_upload(gpry_state* st, int kind, int N, int d, const double* X_train_t,
+                      const double* alpha_, const double* V, double c, const double* ell,
+                      const double* x_min, const double* x_width, double y_mean, double y_std,
+                      double clip_hi) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && X_train_t && alpha_ && V && ell, "NULL argument");
+    upload_model(st, kind, N, d, X_train_t, alpha_, V, nullptr, nullptr, nullptr, c, ell, x_min,
+                 x_width, y_mean, y_std, clip_hi);
+  });
+}
+
+int gpry_state_adopt_factorization(gpry_state* st, double c, const double* ell,
+                                   const double* x_min, const double* x_width, double y_mean,
+                                   double y_std, double clip_hi) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && ell, "NULL argument");
+    if (!st->f_valid)
+      throw GpryError{GPRY_ERR_STATE, "no device-resident factorization to adopt"};
+    const int N = st->f_N, d = st->f_d;
+    std::vector<double> Xt((size_t)N * d);
+    GPRY_CUDA(cudaMemcpy(Xt.data(), st->f_vec.p + 4 * (size_t)N, (size_t)N * d * 8,
+                         cudaMemcpyDeviceToHost));
+    upload_model(st, st->f_kind, N, d, Xt.data(), nullptr, nullptr, nullptr, st->f_VT.p,
+                 st->f_vec.p /* alpha_ */, c, ell, x_min, x_width, y_mean, y_std, clip_hi);
+  });
+}
+
+int gpry_state_info(const gpry_state* st, int* N, int* d, int* kind) {
+  if (!st || !st->loaded) {
+    set_last_error("no model uploaded into this state");
+    return GPRY_ERR_STATE;
+  }
+  if (N) *N = st->N;
+  if (d) *d = st->d;
+  if (kind) *kind = st->kind;
+  return GPRY_OK;
+}
+
+static void predict_common(gpry_state* st, const double* X, int64_t M, bool want_mean,
+                           bool want_std, bool want_acq, double zeta, double sigma_n, double y_max,
+                           int where, double* out_mean, double* out_std, double* out_acq,
+                           cudaStream_t s) {
+  GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+  if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+  GPRY_CHECK_ARG(M >= 0, "M < 0");
+  if (M == 0) return;
+  GPRY_CHECK_ARG(X != nullptr, "X is NULL");
+  GPRY_CUDA(cudaSetDevice(st->device));
+  const bool x_dev = where & GPRY_X_ON_DEVICE, o_dev = where & GPRY_OUT_ON_DEVICE;
+  const double* dX = stage_in(st, X, (size_t)M * st->d, x_dev, st->Xdev, s);
+  double *dm = nullptr, *ds = nullptr, *da = nullptr;
+  if (want_mean && out_mean) {
+    if (o_dev) dm = out_mean; else { st->o_mean.reserve(M); dm = st->o_mean.p; }
+  }
+  if (want_std && out_std) {
+    if (o_dev) ds = out_std; else { st->o_std.reserve(M); ds = st->o_std.p; }
+  }
+  if (want_acq && out_acq) {
+    if (o_dev) da = out_acq; else { st->o_acq.reserve(M); da = st->o_acq.p; }
+  }
+  const bool need_var = (ds != nullptr) || (da != nullptr);
+  predict_pipeline(st, dX, M, dm != nullptr, need_var, da != nullptr, zeta, sigma_n, y_max, dm, ds,
+                   da, s);
+  if (!o_dev) {
+    TimedScope ts(st, s, T_D2H, 0);
+    if (dm) GPRY_CUDA(cudaMemcpyAsync(out_mean, dm, M * 8, cudaMemcpyDeviceToHost, s));
+    if (ds) GPRY_CUDA(cudaMemcpyAsync(out_std, ds, M * 8, cudaMemcpyDeviceToHost, s));
+    if (da) GPRY_CUDA(cudaMemcpyAsync(out_acq, da, M * 8, cudaMemcpyDeviceToHost, s));
+  }
+  if (!o_dev || st->profiling) GPRY_CUDA(cudaStreamSynchronize(s));
+  if (st->profiling) resolve_timings(st);
+}
+
+int gpry_predict(gpry_state* st, const double* X, int64_t M, int what, int where,
+                 double* out_mean, double* out_std, void* stream) {
+  return guarded([&] {
+    predict_common(st, X, M, what & GPRY_WANT_MEAN, what & GPRY_WANT_STD, false, 0, 0, 0, where,
+                   out_mean, out_std, nullptr, (cudaStream_t)stream);
+  });
+}
+
+int gpry_predict_logexp(gpry_state* st, const double* X, int64_t M, double zeta, double sigma_n,
+                        double y_max, int where, double* out_mean, double* out_std,
+                        double* out_acq, void* stream) {
+  return guarded([&] {
+    predict_common(st, X, M, true, true, true, zeta, sigma_n, y_max, where, out_mean, out_std,
+                   out_acq, (cudaStream_t)stream);
+  });
+}
+
+int gpry_predict_logexp_topk(gpry_state* st, const double* X, int64_t M, double zeta,
+                             double sigma_n, double y_max, int Kp, int64_t idx_offset, int where,
+                             double* out_acq, int64_t* out_idx, double* out_mean,
+                             double* out_std, double* out_X, int64_t* n_out, void* stream) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr && n_out != nullptr, "NULL argument");
+    if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+    GPRY_CHECK_ARG(Kp >= 1 && Kp <= MAX_TOPK, "Kp must be in [1, 2048]");
+    *n_out = 0;
+    if (M <= 0) return;
+    cudaStream_t s = (cudaStream_t)stream;
+    GPRY_CUDA(cudaSetDevice(st->device));
+    const bool x_dev = where & GPRY_X_ON_DEVICE, o_dev = where & GPRY_OUT_ON_DEVICE;
+    const int d = st->d;
+    const double* dX = stage_in(st, X, (size_t)M * d, x_dev, st->Xdev, s);
+    st->o_mean.reserve(M);
+    st->o_std.reserve(M);
+    st->o_acq.reserve(M);
+    predict_pipeline(st, dX, M, true, true, true, zeta, sigma_n, y_max, st->o_mean.p, st->o_std.p,
+                     st->o_acq.p, s);
+    double* d_keys;
+    int64_t* d_idx;
+    int64_t n = topk_device(st, st->o_acq.p, M, Kp, idx_offset, &d_keys, &d_idx, s);
+    // gather mean/std/X of the survivors into a small device record
+    st->small.reserve((size_t)Kp * (2 + d) + 2 * MAX_DIM);
+    double* g_mean = o_dev && out_mean ? out_mean : st->small.p;
+    double* g_std = o_dev && out_std ? out_std : st->small.p + Kp;
+    double* g_X = o_dev && out_X ? out_X : st->small.p + 2 * (size_t)Kp;
+    gather_topk(st, d_idx, n, idx_offset, dX, d, st->o_mean.p, st->o_std.p,
+                out_mean ? g_mean : nullptr, out_std ? g_std : nullptr, out_X ? g_X : nullptr, s);
+    const cudaMemcpyKind kind = o_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    {
+      TimedScope ts(st, s, T_D2H, 0);
+      if (out_acq) GPRY_CUDA(cudaMemcpyAsync(out_acq, d_keys, n * 8, kind, s));
+      if (out_idx) GPRY_CUDA(cudaMemcpyAsync(out_idx, d_idx, n * 8, kind, s));
+      if (!o_dev) {
+        if (out_mean) GPRY_CUDA(cudaMemcpyAsync(out_mean, g_mean, n * 8, kind, s));
+        if (out_std) GPRY_CUDA(cudaMemcpyAsync(out_std, g_std, n * 8, kind, s));
+        if (out_X) GPRY_CUDA(cudaMemcpyAsync(out_X, g_X, n * d * 8, kind, s));
+      }
+    }
+    *n_out = n;
+    if (!o_dev || st->profiling) GPRY_CUDA(cudaStreamSynchronize(s));
+    if (st->profiling) resolve_timings(st);
+  });
+}
+
+int gpry_topk(gpry_state* st, const double* scores, int64_t M, int Kp, int where,
+              double* out_scores, int64_t* out_idx, int64_t* n_out, void* stream) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && scores && n_out, "NULL argument");
+    *n_out = 0;
+    if (M <= 0) return;
+    cudaStream_t s = (cudaStream_t)stream;
+    GPRY_CUDA(cudaSetDevice(st->device));
+    const bool x_dev = where & GPRY_X_ON_DEVICE, o_dev = where & GPRY_OUT_ON_DEVICE;
+    const double* dS = stage_in(st, scores, (size_t)M, x_dev, st->o_acq, s);
+    double* d_keys;
+    int64_t* d_idx;
+    int64_t n = topk_device(st, dS, M, Kp, 0, &d_keys, &d_idx, s);
+    const cudaMemcpyKind kind = o_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (out_scores) GPRY_CUDA(cudaMemcpyAsync(out_scores, d_keys, n * 8, kind, s));
+    if (out_idx) GPRY_CUDA(cudaMemcpyAsync(out_idx, d_idx, n * 8, kind, s));
+    *n_out = n;
+    if (!o_dev || st->profiling) GPRY_CUDA(cudaStreamSynchronize(s));
+    if (st->profiling) resolve_timings(st);
+  });
+}
+
+int gpry_mean_grad(gpry_state* st, const double* x, double* out_grad) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && x && out_grad, "NULL argument");
+    mean_grad_device(st, x, out_grad);
+  });
+}
+
+int gpry_factorize(gpry_state* st, int kind, int N, int d, const double* X_train_t,
+                   const double* noise2, const double* y_t, const double* theta, double* out_L,
+                   double* out_V, double* out_alpha, double* out_logdet_half, int* info,
+                   int keep_on_device) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && X_train_t && noise2 && y_t && theta && info, "NULL argument");
+    factorize_device(st, kind, N, d, X_train_t, noise2, y_t, theta, out_L, out_V, out_alpha,
+                     out_logdet_half, info, keep_on_device != 0);
+  });
+}
+
+int gpry_lml_batched(gpry_state* st, int kind, int N, int d, const double* X_train_t,
+                     const double* noise2, const double* y_t, const double* thetas, int B,
+                     double* out_lml, double* out_grad, int* out_info) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && X_train_t && noise2 && y_t && thetas && out_lml && out_info,
+                   "NULL argument");
+    GPRY_CHECK_ARG(B >= 1, "B < 1");
+    lml_batched_device(st, kind, N, d, X_train_t, noise2, y_t, thetas, B, out_lml, out_grad,
+                       out_info);
+  });
+}
+
+int gpry_set_profiling(gpry_state* st, int enable) {
+  if (!st) return GPRY_ERR_ARG;
+  st->profiling = enable != 0;
+  return GPRY_OK;
+}
+
+int gpry_get_timings(gpry_state* st, double* out8, int reset) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && out8, "NULL argument");
+    cudaSetDevice(st->device);
+    resolve_timings(st);
+    for (int i = 0; i < T_NCATS; i++) out8[i] = st->t_ms[i];
+    out8[6] = st->n_launches;
+    out8[7] = st->n_contract_launches;
+    if (reset) {
+      for (int i = 0; i < T_NCATS; i++) st->t_ms[i] = 0;
+      st->n_launches = 0;
+      st->n_contract_launches = 0;
+    }
+  });
+}
+
+}  // extern "C"

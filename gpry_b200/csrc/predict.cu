@@ -1,0 +1,718 @@
+// Posterior mean / std / LogExp over a candidate pool -- the candidate-side hot path.
+//
+// Reference arithmetic (GPry 3.0.0): gpr.py:1176-1227 (predict), 1325-1347 (predict_std),
+// acquisition_functions.py:1068-1074 (LogExp.f); kernel values sklearn:kernels.py:971, 1278,
+// 1569-1570 (RBF), 1720-1729 (Matern).
+//
+// Three kernels per chunk of candidates (K* is only ever materialised one chunk at a time,
+// in a tile layout private to this library):
+//
+//   kstar_build   k*[i, j] = c g(|u_i - t_j|) for a tile of 128 candidates x a slice of
+//                 training points; training points (pre-divided by the length scales) are
+//                 staged into shared memory by TMA bulk copy and broadcast to the warp,
+//                 candidate coordinates live in registers.  Emits K* tiles in the
+//                 [k-panel][candidate][4] layout the contraction wants plus the partial
+//                 means sum_j k*_ij alpha_j.                       (FP64 ALU / exp bound)
+//   var_contract  ssq[i] = sum_j (sum_k V[j,k] k*[i,k])^2 with V = L^-1 lower triangular:
+//                 block-lower-triangular GEMM on FP64 tensor cores (mma.sync m8n8k4 ->
+//                 DMMA.8x8x4), operands streamed by TMA bulk copies through a 6-stage
+//                 mbarrier ring, squared-row-sum epilogue kept in registers.  (DMMA bound)
+//   finish        var = c - ssq, clamp, sqrt, de-normalise, clip, LogExp.
+#include <math.h>
+
+#include "state.cuh"
+
+namespace gpry {
+
+// ---------------------------------------------------------------------------------------
+// stationary kernel g(r2) * c
+// ---------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ double kernel_value(double r2, double c) {
+  if (KIND == GPRY_KERNEL_RBF) {
+    return c * exp(-0.5 * r2);                        // sklearn:kernels.py:1570
+  } else if (KIND == GPRY_KERNEL_MATERN15) {
+    double K = sqrt(r2) * 1.7320508075688772;         // dists * sqrt(3)   :1725
+    return c * ((1.0 + K) * exp(-K));                 // :1726
+  } else {
+    double K = sqrt(r2) * 2.23606797749979;           // dists * sqrt(5)   :1728
+    return c * ((1.0 + K + K * K / 3.0) * exp(-K));   // :1729
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// kstar_build
+//   grid  = (tiles in chunk, JS)      block = 128 threads = the 128 candidates of a tile
+//   each block: NJ = Npad / JS training points (a multiple of 16)
+// ---------------------------------------------------------------------------------------
+template <int DP, int KIND, bool WRITE_KS>
+__global__ void __launch_bounds__(128)
+kstar_build_kernel(const double* __restrict__ X, int64_t M, int d, int64_t cand0,
+                   const double* __restrict__ T, const double* __restrict__ alpha, int NJ,
+                   int nKT, double c, XformParams prm, double* __restrict__ Ks,
+                   double* __restrict__ meanp, int chunk_cands) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Ts = reinterpret_cast<double*>(smem_raw);          // [NJ][DP]
+  double* As = Ts + (size_t)NJ * DP;                         // [NJ]
+  double* Xs = As + NJ;                                      // [128][d]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Xs + 128 * d + (d & 1));
+
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int j0 = blockIdx.y * NJ;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytesT = (uint32_t)NJ * DP * 8, bytesA = (uint32_t)NJ * 8;
+    mbar_expect_tx(bar, bytesT + bytesA);
+    tma_bulk_g2s(Ts, T + (size_t)j0 * DP, bytesT, bar);
+    tma_bulk_g2s(As, alpha + j0, bytesA, bar);
+  }
+  // coalesced load of the candidate tile (contiguous 128 * d doubles)
+  const int64_t cbase = cand0 + (int64_t)tile * TILE_ROWS;
+  const int64_t avail = (M - cbase) * d;   // doubles available from X + cbase*d
+  const double* Xg = X + cbase * d;
+  for (int e = tid; e < TILE_ROWS * d; e += 128) Xs[e] = (e < avail) ? __ldg(Xg + e) : 0.0;
+  __syncthreads();
+
+  // ((x - min) / width) / ell : preprocessing.py:380 then sklearn:kernels.py:1569 (X / l)
+  double u[DP];
+#pragma unroll
+  for (int k = 0; k < DP; k++) {
+    if (k < d) {
+      double x = Xs[tid * d + k];
+      u[k] = ((x - prm.x_min[k]) / prm.x_width[k]) / prm.ell[k];
+    } else {
+      u[k] = 0.0;
+    }
+  }
+  mbar_wait(bar, 0);
+
+  double mp = 0.0;
+  double* kout = Ks + ((size_t)tile * nKT + (j0 >> 4)) * TILE_DOUBLES + tid * 4;
+  for (int j4 = 0; j4 < NJ; j4 += 4) {
+    double kv[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const double2* tp = reinterpret_cast<const double2*>(Ts + (size_t)(j4 + jj) * DP);
+      double r2 = 0.0;
+#pragma unroll
+      for (int k2 = 0; k2 < DP / 2; k2++) {
+        double2 t = tp[k2];
+        double d0 = u[2 * k2] - t.x;
+        r2 = fma(d0, d0, r2);
+        double d1 = u[2 * k2 + 1] - t.y;
+        r2 = fma(d1, d1, r2);
+      }
+      kv[jj] = kernel_value<KIND>(r2, c);
+      mp = fma(kv[jj], As[j4 + jj], mp);
+    }
+    if (WRITE_KS) {
+      // tile (j4 / 16), panel (j4 / 4) % 4, row tid
+      double* p = kout + (size_t)(j4 >> 4) * TILE_DOUBLES + ((j4 >> 2) & 3) * (TILE_ROWS * 4);
+      reinterpret_cast<double2*>(p)[0] = make_double2(kv[0], kv[1]);
+      reinterpret_cast<double2*>(p)[1] = make_double2(kv[2], kv[3]);
+    }
+  }
+  meanp[(size_t)blockIdx.y * chunk_cands + tile * TILE_ROWS + tid] = mp;
+}
+
+// generic-d variant (d > 32): candidate coordinates stay in shared memory
+template <int KIND, bool WRITE_KS>
+__global__ void __launch_bounds__(128)
+kstar_build_generic_kernel(const double* __restrict__ X, int64_t M, int d, int DP, int64_t cand0,
+                           const double* __restrict__ T, const double* __restrict__ alpha,
+                           int NJ, int nKT, double c, const double* __restrict__ prm,
+                           double* __restrict__ Ks, double* __restrict__ meanp,
+                           int chunk_cands) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Ts = reinterpret_cast<double*>(smem_raw);   // [NJ][DP]
+  double* As = Ts + (size_t)NJ * DP;                  // [NJ]
+  double* Us = As + NJ;                               // [DP][129]  (transposed, padded)
+  const int tid = threadIdx.x, tile = blockIdx.x, j0 = blockIdx.y * NJ;
+  for (int e = tid; e < NJ * DP; e += 128) Ts[e] = T[(size_t)j0 * DP + e];
+  for (int e = tid; e < NJ; e += 128) As[e] = alpha[j0 + e];
+  const int64_t cbase = cand0 + (int64_t)tile * TILE_ROWS;
+  const int64_t cand = cbase + tid;
+  for (int k = 0; k < DP; k++) {
+    double v = 0.0;
+    if (k < d && cand < M) {
+      double x = X[cand * d + k];
+      v = ((x - prm[k]) / prm[MAX_DIM + k]) / prm[2 * MAX_DIM + k];
+    }
+    Us[k * 129 + tid] = v;
+  }
+  __syncthreads();
+  double mp = 0.0;
+  double* kout = Ks + ((size_t)tile * nKT + (j0 >> 4)) * TILE_DOUBLES + tid * 4;
+  for (int j4 = 0; j4 < NJ; j4 += 4) {
+    double kv[4];
+    for (int jj = 0; jj < 4; jj++) {
+      const double* tp = Ts + (size_t)(j4 + jj) * DP;
+      double r2 = 0.0;
+      for (int k = 0; k < DP; k++) {
+        double d0 = Us[k * 129 + tid] - tp[k];
+        r2 = fma(d0, d0, r2);
+      }
+      kv[jj] = kernel_value<KIND>(r2, c);
+      mp = fma(kv[jj], As[j4 + jj], mp);
+    }
+    if (WRITE_KS) {
+      double* p = kout + (size_t)(j4 >> 4) * TILE_DOUBLES + ((j4 >> 2) & 3) * (TILE_ROWS * 4);
+      reinterpret_cast<double2*>(p)[0] = make_double2(kv[0], kv[1]);
+      reinterpret_cast<double2*>(p)[1] = make_double2(kv[2], kv[3]);
+    }
+  }
+  meanp[(size_t)blockIdx.y * chunk_cands + tile * TILE_ROWS + tid] = mp;
+}
+
+// ---------------------------------------------------------------------------------------
+// var_contract
+// ---------------------------------------------------------------------------------------
+constexpr int VC_STAGES = 6;
+constexpr int VC_WARPS = 8;
+constexpr int VC_THREADS = VC_WARPS * 32;
+
+struct VcSmem {
+  double A[VC_STAGES][TILE_DOUBLES];   // V tiles      [4 panels][128 rows][4]
+  double B[VC_STAGES][TILE_DOUBLES];   // K* tiles     [4 panels][128 cands][4]
+  double red[2][TILE_ROWS];
+  uint64_t full[VC_STAGES];
+  uint64_t empty[VC_STAGES];
+};
+
+// which row-split owns row block jb (snake order: balanced triangular work)
+__device__ __forceinline__ int row_block_owner(int jb, int S) {
+  int pos = jb % (2 * S);
+  return pos < S ? pos : 2 * S - 1 - pos;
+}
+__device__ __forceinline__ int next_owned_block(int jb, int nJ, int S, int split) {
+  while (jb < nJ && row_block_owner(jb, S) != split) jb++;
+  return jb;
+}
+
+// The (tile, row block, k-tile) sequence a CTA walks; used by the TMA issuer, which runs
+// VC_STAGES - 1 steps ahead of the MMA loop.
+struct VcSeq {
+  int t, jb, kt, kt_end;
+  __device__ __forceinline__ void start(int n_tiles, int nJ, int S, int split, int kt_total) {
+    t = blockIdx.x;
+    jb = next_owned_block(0, nJ, S, split);
+    kt = 0;
+    kt_end = min((jb + 1) * KT_PER_BLOCK, kt_total);
+    if (jb >= nJ) t = n_tiles;
+  }
+  __device__ __forceinline__ bool valid(int n_tiles) const { return t < n_tiles; }
+  __device__ __forceinline__ void advance(int nJ, int S, int split, int kt_total) {
+    if (++kt < kt_end) return;
+    kt = 0;
+    jb = next_owned_block(jb + 1, nJ, S, split);
+    if (jb >= nJ) {
+      t += gridDim.x;
+      jb = next_owned_block(0, nJ, S, split);
+    }
+    kt_end = min((jb + 1) * KT_PER_BLOCK, kt_total);
+  }
+};
+
+// grid = (min(tiles, #SM), row_splits); 256 threads = 8 MMA warps (warp tile 64 rows x 32
+// candidates, 32 DMMA accumulator fragments); lane 0 of warp 0 doubles as the TMA issuer.
+__global__ void __launch_bounds__(VC_THREADS, 1)
+var_contract_kernel(const double* __restrict__ Vt, const double* __restrict__ Ks, int n_tiles,
+                    int N, int nJ, int nKT, int row_splits, double* __restrict__ ssqp,
+                    int chunk_cands) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  VcSmem& sm = *reinterpret_cast<VcSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.y;
+  const int kt_total = (N + TILE_K - 1) / TILE_K;   // k-tiles that contain real columns
+
+  if (tid == 0) {
+    for (int s = 0; s < VC_STAGES; s++) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], VC_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // ---- TMA issuer state (thread 0 only) ----
+  VcSeq pseq;
+  int pstage = 0;
+  uint32_t pphase = 0;
+  auto produce_one = [&]() {
+    mbar_wait(&sm.empty[pstage], pphase ^ 1);
+    mbar_expect_tx(&sm.full[pstage], 2 * TILE_BYTES);
+    tma_bulk_g2s(sm.A[pstage], Vt + (vtile_index(pseq.jb, 0) + pseq.kt) * TILE_DOUBLES,
+                 TILE_BYTES, &sm.full[pstage]);
+    tma_bulk_g2s(sm.B[pstage], Ks + ((size_t)pseq.t * nKT + pseq.kt) * TILE_DOUBLES, TILE_BYTES,
+                 &sm.full[pstage]);
+    if (++pstage == VC_STAGES) {
+      pstage = 0;
+      pphase ^= 1;
+    }
+    pseq.advance(nJ, row_splits, split, kt_total);
+  };
+  if (tid == 0) {
+    pseq.start(n_tiles, nJ, row_splits, split, kt_total);
+    for (int i = 0; i < VC_STAGES - 1 && pseq.valid(n_tiles); i++) produce_one();
+  }
+
+  const int rw = warp >> 2;        // row half   (rows rw*64 .. +63 of the row block)
+  const int cw = warp & 3;         // candidate quarter (cands cw*32 .. +31)
+  int stage = 0;
+  uint32_t phase = 0;
+
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    double ssq[4][2];
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) ssq[ni][0] = ssq[ni][1] = 0.0;
+
+    for (int jb = next_owned_block(0, nJ, row_splits, split); jb < nJ;
+         jb = next_owned_block(jb + 1, nJ, row_splits, split)) {
+      const int kt_end = min((jb + 1) * KT_PER_BLOCK, kt_total);
+      // this warp's rows need columns k <= row, i.e. k-tiles below kt_need; rows >= N are 0
+      const int row0 = jb * TILE_ROWS + rw * 64;
+      const int kt_need = (row0 >= N) ? 0 : min(kt_end, (row0 + 64) / TILE_K);
+
+      double acc[8][4][2];
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+      for (int kt = 0; kt < kt_end; kt++) {
+        if (tid == 0 && pseq.valid(n_tiles)) produce_one();   // refill the slot freed last step
+        __syncwarp();
+        mbar_wait(&sm.full[stage], phase);
+        if (kt < kt_need) {
+          const double* As = sm.A[stage] + (rw * 64) * 4 + lane;
+          const double* Bs = sm.B[stage] + (cw * 32) * 4 + lane;
+#pragma unroll
+          for (int p = 0; p < 4; p++) {
+            double a[8], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++) a[mi] = As[p * (TILE_ROWS * 4) + mi * 32];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) b[ni] = Bs[p * (TILE_ROWS * 4) + ni * 32];
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+              for (int ni = 0; ni < 4; ni++)
+                dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        if (++stage == VC_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      // squared-row-sum epilogue (gpr.py:1208 einsum("ji,ji->i", M, M)), kept per lane
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+          ssq[ni][0] = fma(acc[mi][ni][0], acc[mi][ni][0], ssq[ni][0]);
+          ssq[ni][1] = fma(acc[mi][ni][1], acc[mi][ni][1], ssq[ni][1]);
+        }
+    }
+
+    // reduce over the 8 row groups of the warp (lanes with equal lane%4), then over rw
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        double v = ssq[ni][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (lane < 4) sm.red[rw][cw * 32 + ni * 8 + 2 * lane + e] = v;
+      }
+    __syncthreads();
+    if (tid < TILE_ROWS)
+      ssqp[(size_t)split * chunk_cands + (size_t)t * TILE_ROWS + tid] =
+          sm.red[0][tid] + sm.red[1][tid];
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// finish: gpr.py:1180-1195, 1207-1227 and LogExp.f acquisition_functions.py:1071-1074
+// ---------------------------------------------------------------------------------------
+__global__ void finish_kernel(const double* __restrict__ meanp, int JS,
+                              const double* __restrict__ ssqp, int row_splits, int chunk_cands,
+                              int n, double c, double y_mean, double y_std, double clip_hi,
+                              int want_acq, double two_zeta, double sigma_n2, double y_max,
+                              double* __restrict__ o_mean, double* __restrict__ o_std,
+                              double* __restrict__ o_acq) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double m_ = 0.0;
+  for (int s = 0; s < JS; s++) m_ += meanp[(size_t)s * chunk_cands + i];
+  double mean = m_ * y_std + y_mean;              // preprocessing.py:620
+  mean = fmin(mean, clip_hi);                     // gpr.py:1187-1195 (np.clip upper)
+  if (isnan(m_)) mean = m_;
+  if (o_mean) o_mean[i] = mean;
+  if (ssqp) {
+    double ssq = 0.0;
+    for (int s = 0; s < row_splits; s++) ssq += ssqp[(size_t)s * chunk_cands + i];
+    double var = c - ssq;                         // gpr.py:1207-1208
+    if (var < 0.0) var = 0.0;                     // :1214-1219
+    double std = sqrt(var) * y_std;               // :1220, preprocessing.py:630
+    if (o_std) o_std[i] = std;
+    if (want_acq && o_acq) {
+      double v = std * std - sigma_n2;            // std**2 - noise_level**2
+      v = v > 0.0 ? v : 0.0;                      // np.clip(., 0, None)
+      o_acq[i] = two_zeta * (mean - y_max) + log(sqrt(v));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// mean gradient at one point: kernels.py:257-278 (RBF), 363-393 (nu=1.5), 395-432 (nu=2.5),
+// Product rule :687-699, gpr.py:1237-1242.   grid = d blocks, block k reduces dimension k.
+// ---------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256)
+mean_grad_kernel(const double* __restrict__ Xt, const double* __restrict__ alpha, int N, int d,
+                 const double* __restrict__ x_t /* transformed point */,
+                 const double* __restrict__ ell, double c, double y_std,
+                 double* __restrict__ out) {
+  __shared__ double red[256];
+  const int k = blockIdx.x;
+  double s = 0.0;
+  for (int j = threadIdx.x; j < N; j += 256) {
+    double r2 = 0.0, dk = 0.0;
+    for (int q = 0; q < d; q++) {
+      double diff = (x_t[q] - Xt[(size_t)j * d + q]) / ell[q];
+      r2 = fma(diff, diff, r2);
+      if (q == k) dk = diff;
+    }
+    double g;
+    if (KIND == GPRY_KERNEL_RBF) {
+      g = (-exp(-0.5 * r2) * dk) / ell[k];
+    } else if (KIND == GPRY_KERNEL_MATERN15) {
+      double dist = sqrt(r2);
+      double s3d = 1.7320508075688772 * dist;
+      double by = dist != 0.0 ? 1.7320508075688772 / dist : 0.0;
+      double f_grad = (dk / ell[k]) * by;
+      g = exp(-s3d) * f_grad * (1.0 - (1.0 + s3d));
+    } else {
+      double dist = sqrt(r2);
+      double s5d = 2.23606797749979 * dist;
+      double f = (5.0 / 3.0) * r2 + s5d + 1.0;
+      double inv = dist != 0.0 ? 2.23606797749979 * (1.0 / dist) : 0.0;
+      double dl = dk / ell[k];
+      double f1g = inv * dl, f2g = (10.0 / 3.0) * dl;
+      double gg = exp(-s5d);
+      g = f * (-gg * f1g) + gg * (f1g + f2g);
+    }
+    s = fma(c * g, alpha[j], s);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[k] = red[0] * y_std;
+}
+
+// ---------------------------------------------------------------------------------------
+// model upload helpers
+// ---------------------------------------------------------------------------------------
+// T[j][k] = X_train_[j][k] / ell[k], zero padded to [Npad][DP]
+__global__ void scale_train_kernel(const double* __restrict__ Xt, int N, int d, int Npad, int DP,
+                                   const double* __restrict__ ell, double* __restrict__ T) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Npad * DP) return;
+  int j = (int)(e / DP), k = (int)(e % DP);
+  T[e] = (j < N && k < d) ? Xt[(size_t)j * d + k] / ell[k] : 0.0;
+}
+
+// pack row-major V (lower triangular N x N, leading dimension ld; or its transpose) into
+// the tile layout.  One thread per packed element.
+__global__ void pack_v_kernel(const double* __restrict__ V, int N, int ld, int transposed, int nJ,
+                              double* __restrict__ Vt) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = vtile_count(nJ) * TILE_DOUBLES;
+  if (e >= total) return;
+  int64_t tile = e / TILE_DOUBLES;
+  int within = (int)(e % TILE_DOUBLES);
+  // invert vtile_index: find jb with 4*jb*(jb+1) <= tile
+  int jb = (int)((sqrt(1.0 + (double)tile) - 1.0) * 0.5);
+  while (vtile_index(jb + 1, 0) <= tile) jb++;
+  while (vtile_index(jb, 0) > tile) jb--;
+  int kt = (int)(tile - vtile_index(jb, 0));
+  int p = within / (TILE_ROWS * 4), rem = within % (TILE_ROWS * 4);
+  int r = rem >> 2, kk = rem & 3;
+  int row = jb * TILE_ROWS + r, col = kt * TILE_K + p * 4 + kk;
+  double v = 0.0;
+  if (row < N && col <= row)
+    v = transposed ? V[(size_t)col * ld + row] : V[(size_t)row * ld + col];
+  Vt[e] = v;
+}
+
+__global__ void pad_copy_kernel(const double* __restrict__ src, int n, int npad,
+                                double* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npad) dst[i] = i < n ? src[i] : 0.0;
+}
+
+void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_t,
+                  const double* alpha_, const double* V_host, const double* V_dev_rowmajor,
+                  const double* VT_dev_rowmajor, const double* alpha_dev, double c,
+                  const double* ell, const double* x_min, const double* x_width, double y_mean,
+                  double y_std, double clip_hi) {
+  GPRY_CHECK_ARG(kind >= 0 && kind <= 2, "unknown kernel kind");
+  GPRY_CHECK_ARG(N >= 1 && d >= 1 && d <= MAX_DIM, "need N >= 1 and 1 <= d <= 128");
+  GPRY_CUDA(cudaSetDevice(st->device));
+  st->loaded = false;
+  st->kind = kind;
+  st->N = N;
+  st->d = d;
+  st->DP = round_up(d, 4);
+  st->Npad = round_up(N, TILE_ROWS);
+  st->nJ = st->Npad / TILE_ROWS;
+  st->nKT = st->Npad / TILE_K;
+  st->c = c;
+  st->y_mean = y_mean;
+  st->y_std = y_std;
+  st->clip_hi = clip_hi;
+  std::vector<double> prm(3 * MAX_DIM, 1.0);
+  for (int k = 0; k < d; k++) {
+    prm[k] = x_min ? x_min[k] : 0.0;
+    prm[MAX_DIM + k] = x_width ? x_width[k] : 1.0;
+    prm[2 * MAX_DIM + k] = ell[k];
+    if (k < MAX_DIM_REG) {
+      st->prm.x_min[k] = prm[k];
+      st->prm.x_width[k] = prm[MAX_DIM + k];
+      st->prm.ell[k] = ell[k];
+    }
+  }
+  for (int k = d; k < MAX_DIM_REG; k++) {
+    st->prm.x_min[k] = 0.0;
+    st->prm.x_width[k] = 1.0;
+    st->prm.ell[k] = 1.0;
+  }
+  cudaStream_t s = 0;
+  st->prm_dev.reserve(3 * MAX_DIM);
+  GPRY_CUDA(cudaMemcpyAsync(st->prm_dev.p, prm.data(), 3 * MAX_DIM * 8, cudaMemcpyHostToDevice, s));
+  st->Xt.reserve((size_t)N * d);
+  GPRY_CUDA(cudaMemcpyAsync(st->Xt.p, X_train_t, (size_t)N * d * 8, cudaMemcpyHostToDevice, s));
+  st->T.reserve((size_t)st->Npad * st->DP);
+  {
+    int64_t total = (int64_t)st->Npad * st->DP;
+    scale_train_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        st->Xt.p, N, d, st->Npad, st->DP, st->prm_dev.p + 2 * MAX_DIM, st->T.p);
+    GPRY_CUDA(cudaGetLastError());
+  }
+  st->alpha.reserve(st->Npad);
+  if (alpha_dev) {
+    pad_copy_kernel<<<(st->Npad + 255) / 256, 256, 0, s>>>(alpha_dev, N, st->Npad, st->alpha.p);
+    GPRY_CUDA(cudaGetLastError());
+  } else {
+    GPRY_CUDA(cudaMemsetAsync(st->alpha.p, 0, (size_t)st->Npad * 8, s));
+    GPRY_CUDA(cudaMemcpyAsync(st->alpha.p, alpha_, (size_t)N * 8, cudaMemcpyHostToDevice, s));
+  }
+  const double* Vsrc = V_dev_rowmajor;
+  int transposed = 0;
+  if (V_host) {
+    st->tmp.reserve((size_t)N * N);
+    GPRY_CUDA(cudaMemcpyAsync(st->tmp.p, V_host, (size_t)N * N * 8, cudaMemcpyHostToDevice, s));
+    Vsrc = st->tmp.p;
+  } else if (VT_dev_rowmajor) {
+    Vsrc = VT_dev_rowmajor;
+    transposed = 1;
+  }
+  GPRY_CHECK_ARG(Vsrc != nullptr, "no V given");
+  int64_t total = vtile_count(st->nJ) * TILE_DOUBLES;
+  st->Vt.reserve((size_t)total);
+  pack_v_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Vsrc, N, N, transposed, st->nJ,
+                                                               st->Vt.p);
+  GPRY_CUDA(cudaGetLastError());
+  GPRY_CUDA(cudaStreamSynchronize(s));
+  st->loaded = true;
+}
+
+// ---------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------
+template <int KIND, bool WRITE_KS>
+static void launch_build(gpry_state* st, const double* dX, int64_t M, int64_t cand0, int tiles,
+                         int JS, int chunk_cands, cudaStream_t s) {
+  const int NJ = st->Npad / JS;
+  const int d = st->d, DP = st->DP;
+  dim3 grid(tiles, JS), block(128);
+  if (d <= MAX_DIM_REG) {
+    size_t smem = ((size_t)NJ * DP + NJ + 128 * d + (d & 1)) * 8 + 16;
+#define GPRY_LAUNCH_BUILD(DPV)                                                                \
+  case DPV: {                                                                                 \
+    auto kern = kstar_build_kernel<DPV, KIND, WRITE_KS>;                                      \
+    if (smem > 48 * 1024)                                                                     \
+      GPRY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                     (int)smem));                                             \
+    kern<<<grid, block, smem, s>>>(dX, M, d, cand0, st->T.p, st->alpha.p, NJ, st->nKT, st->c, \
+                                   st->prm, st->Ks.p, st->meanp.p, chunk_cands);              \
+  } break;
+    switch (DP) {
+      GPRY_LAUNCH_BUILD(4)
+      GPRY_LAUNCH_BUILD(8)
+      GPRY_LAUNCH_BUILD(12)
+      GPRY_LAUNCH_BUILD(16)
+      GPRY_LAUNCH_BUILD(20)
+      GPRY_LAUNCH_BUILD(24)
+      GPRY_LAUNCH_BUILD(28)
+      GPRY_LAUNCH_BUILD(32)
+      default:
+        throw GpryError{GPRY_ERR_ARG, "internal: bad DP"};
+    }
+#undef GPRY_LAUNCH_BUILD
+  } else {
+    size_t smem = ((size_t)NJ * DP + NJ + (size_t)DP * 129) * 8;
+    auto kern = kstar_build_generic_kernel<KIND, WRITE_KS>;
+    GPRY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, block, smem, s>>>(dX, M, d, DP, cand0, st->T.p, st->alpha.p, NJ, st->nKT, st->c,
+                                   st->prm_dev.p, st->Ks.p, st->meanp.p, chunk_cands);
+  }
+  GPRY_CUDA(cudaGetLastError());
+}
+
+template <bool WRITE_KS>
+static void launch_build_kind(gpry_state* st, const double* dX, int64_t M, int64_t cand0,
+                              int tiles, int JS, int chunk_cands, cudaStream_t s) {
+  switch (st->kind) {
+    case GPRY_KERNEL_RBF:
+      launch_build<GPRY_KERNEL_RBF, WRITE_KS>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
+      break;
+    case GPRY_KERNEL_MATERN15:
+      launch_build<GPRY_KERNEL_MATERN15, WRITE_KS>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
+      break;
+    default:
+      launch_build<GPRY_KERNEL_MATERN25, WRITE_KS>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
+  }
+}
+
+// Largest j-split count JS (power of two) such that the per-block training slice
+// NJ = Npad / JS stays a multiple of 16, fits in shared memory and gives >= ~2 blocks/SM.
+static int choose_jsplit(const gpry_state* st, int tiles) {
+  int JS = 1;
+  if (st->d > MAX_DIM_REG) {   // generic path: [NJ][DP] slice + [DP][129] candidates in smem
+    int maxJSg = st->Npad / 16;
+    while (JS < maxJSg && ((size_t)(st->Npad / JS) * (st->DP + 1) * 8 > 64 * 1024)) JS *= 2;
+    return JS;
+  }
+  const int maxJS = st->Npad / 128;   // NJ >= 128
+  // shared-memory bound on NJ (keep a block under ~48 KB so several are resident per SM)
+  while (JS < maxJS && ((size_t)(st->Npad / JS) * (st->DP + 1) * 8 > 40 * 1024)) JS *= 2;
+  while (JS * 2 <= maxJS && (int64_t)tiles * JS < 4 * st->n_sm && (st->Npad / (JS * 2)) % 16 == 0)
+    JS *= 2;
+  while (JS > 1 && (st->Npad % JS != 0 || (st->Npad / JS) % 16 != 0)) JS /= 2;
+  return JS;
+}
+
+void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mean, bool want_var,
+                      bool want_acq, double zeta, double sigma_n, double y_max, double* d_mean,
+                      double* d_std, double* d_acq, cudaStream_t s) {
+  if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+  if (M <= 0) return;
+  GPRY_CUDA(cudaSetDevice(st->device));
+  const int64_t total_tiles = (M + TILE_ROWS - 1) / TILE_ROWS;
+  // chunking: at most 2 waves of tiles per chunk (bounds the K* scratch: 2 MB/tile at N=2048)
+  const int max_chunk_tiles = 2 * st->n_sm;
+  const int chunk_tiles = (int)std::min<int64_t>(total_tiles, max_chunk_tiles);
+  const int chunk_cands = chunk_tiles * TILE_ROWS;
+  // row splits: for small pools spread the row blocks of V over more CTAs
+  int row_splits = 1;
+  if (want_var) {
+    while (row_splits * 2 <= st->nJ && (int64_t)chunk_tiles * row_splits * 2 <= st->n_sm)
+      row_splits *= 2;
+  }
+  const int JS = choose_jsplit(st, chunk_tiles);
+  if (want_var) st->Ks.reserve((size_t)chunk_tiles * st->nKT * TILE_DOUBLES);
+  st->meanp.reserve((size_t)JS * chunk_cands);
+  if (want_var) st->ssqp.reserve((size_t)row_splits * chunk_cands);
+  if (want_var)
+    GPRY_CUDA(cudaFuncSetAttribute(var_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(VcSmem)));
+  for (int64_t t0 = 0; t0 < total_tiles; t0 += chunk_tiles) {
+    const int tiles = (int)std::min<int64_t>(chunk_tiles, total_tiles - t0);
+    const int64_t cand0 = t0 * TILE_ROWS;
+    const int n = (int)std::min<int64_t>((int64_t)tiles * TILE_ROWS, M - cand0);
+    {
+      TimedScope ts(st, s, T_BUILD);
+      if (want_var)
+        launch_build_kind<true>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
+      else
+        launch_build_kind<false>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
+    }
+    if (want_var) {
+      TimedScope ts(st, s, T_CONTRACT);
+      st->n_contract_launches += 1;
+      dim3 grid(std::min(tiles, st->n_sm), row_splits);
+      var_contract_kernel<<<grid, VC_THREADS, sizeof(VcSmem), s>>>(
+          st->Vt.p, st->Ks.p, tiles, st->N, st->nJ, st->nKT, row_splits, st->ssqp.p, chunk_cands);
+      GPRY_CUDA(cudaGetLastError());
+    }
+    {
+      TimedScope ts(st, s, T_FINISH);
+      finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(
+          st->meanp.p, JS, want_var ? st->ssqp.p : nullptr, row_splits, chunk_cands, n, st->c,
+          st->y_mean, st->y_std, st->clip_hi, want_acq ? 1 : 0, 2.0 * zeta, sigma_n * sigma_n,
+          y_max, d_mean ? d_mean + cand0 : nullptr,
+          d_std ? d_std + cand0 : nullptr, d_acq ? d_acq + cand0 : nullptr);
+      GPRY_CUDA(cudaGetLastError());
+    }
+  }
+}
+
+void mean_grad_device(gpry_state* st, const double* x_host, double* out_host) {
+  if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+  GPRY_CUDA(cudaSetDevice(st->device));
+  const int d = st->d;
+  std::vector<double> xt(d);
+  // Normalize_bounds.transform, preprocessing.py:380 (same expression as the reference)
+  for (int k = 0; k < d; k++) {
+    double mn, w;
+    if (d <= MAX_DIM_REG) {
+      mn = st->prm.x_min[k];
+      w = st->prm.x_width[k];
+    } else {
+      std::vector<double> prm(3 * MAX_DIM);
+      GPRY_CUDA(cudaMemcpy(prm.data(), st->prm_dev.p, 3 * MAX_DIM * 8, cudaMemcpyDeviceToHost));
+      mn = prm[k];
+      w = prm[MAX_DIM + k];
+    }
+    xt[k] = (x_host[k] - mn) / w;
+  }
+  st->small.reserve(2 * MAX_DIM);
+  cudaStream_t s = 0;
+  GPRY_CUDA(cudaMemcpyAsync(st->small.p, xt.data(), d * 8, cudaMemcpyHostToDevice, s));
+  const double* ell = st->prm_dev.p + 2 * MAX_DIM;
+  double* out = st->small.p + MAX_DIM;
+  switch (st->kind) {
+    case GPRY_KERNEL_RBF:
+      mean_grad_kernel<GPRY_KERNEL_RBF><<<d, 256, 0, s>>>(st->Xt.p, st->alpha.p, st->N, d,
+                                                         st->small.p, ell, st->c, st->y_std, out);
+      break;
+    case GPRY_KERNEL_MATERN15:
+      mean_grad_kernel<GPRY_KERNEL_MATERN15><<<d, 256, 0, s>>>(
+          st->Xt.p, st->alpha.p, st->N, d, st->small.p, ell, st->c, st->y_std, out);
+      break;
+    default:
+      mean_grad_kernel<GPRY_KERNEL_MATERN25><<<d, 256, 0, s>>>(
+          st->Xt.p, st->alpha.p, st->N, d, st->small.p, ell, st->c, st->y_std, out);
+  }
+  GPRY_CUDA(cudaGetLastError());
+  GPRY_CUDA(cudaMemcpyAsync(out_host, out, d * 8, cudaMemcpyDeviceToHost, s));
+  GPRY_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace gpry

@@ -1,0 +1,141 @@
+// Device-resident model state and scratch management for the gpry_b200 library.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace gpry {
+
+constexpr int MAX_DIM = 128;      // supported input dimensionality
+constexpr int MAX_DIM_REG = 32;   // dimensionality handled with coordinates in registers
+constexpr int MAX_TOPK = 2048;    // largest K' of the fused ranking
+
+// per-dimension affine transform + length scales, passed by value to kernels
+struct XformParams {
+  double x_min[MAX_DIM_REG];
+  double x_width[MAX_DIM_REG];
+  double ell[MAX_DIM_REG];
+};
+
+enum TimingCat { T_BUILD = 0, T_CONTRACT = 1, T_FINISH = 2, T_TOPK = 3, T_H2D = 4, T_D2H = 5,
+                 T_NCATS = 6 };
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    if (p) GPRY_CUDA(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      want = n;
+      e = cudaMalloc((void**)&p, want * sizeof(T));
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      throw GpryError{GPRY_ERR_NOMEM, "device allocation of " +
+                                          std::to_string(want * sizeof(T)) + " bytes failed"};
+    }
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct EventPair {
+  int cat;
+  cudaEvent_t e0, e1;
+};
+
+}  // namespace gpry
+
+struct gpry_state {
+  int device = 0;
+  int n_sm = 148;
+  bool loaded = false;
+
+  // model
+  int kind = 0, N = 0, d = 0;
+  int DP = 0;     // d padded to a multiple of 4
+  int Npad = 0;   // N padded to a multiple of 128
+  int nJ = 0;     // row blocks of V (Npad / 128)
+  int nKT = 0;    // k-tiles per candidate tile (Npad / 16)
+  double c = 1.0, y_mean = 0.0, y_std = 1.0, clip_hi = 0.0;
+  gpry::XformParams prm;                 // valid when d <= MAX_DIM_REG
+  gpry::DevBuf<double> prm_dev;          // [3][MAX_DIM] x_min, x_width, ell (generic-d path)
+  gpry::DevBuf<double> T;                // [Npad][DP]  X_train_ / ell   (zero padded)
+  gpry::DevBuf<double> Xt;               // [N][d]      X_train_ (un-scaled, gradient kernel)
+  gpry::DevBuf<double> alpha;            // [Npad]
+  gpry::DevBuf<double> Vt;               // tiled lower block triangle of V = L^-1
+
+  // scratch (grown on demand, reused across calls)
+  gpry::DevBuf<double> Ks;               // [chunk_tiles][nKT] K* tiles
+  gpry::DevBuf<double> meanp;            // [JS][chunk_cands]
+  gpry::DevBuf<double> ssqp;             // [row_splits][chunk_cands]
+  gpry::DevBuf<double> Xdev;             // staged candidates (host input)
+  gpry::DevBuf<double> o_mean, o_std, o_acq;   // per-candidate outputs (device)
+  gpry::DevBuf<double> tk_keys[2];
+  gpry::DevBuf<int64_t> tk_idx[2];
+  gpry::DevBuf<double> tmp;              // upload staging (raw V etc.)
+  gpry::DevBuf<double> small;            // small outputs (gradient, top-k records)
+
+  // training-side residency (train.cu)
+  gpry::DevBuf<double> f_K, f_VT, f_W, f_vec;
+  int f_N = 0, f_d = 0, f_kind = -1;
+  bool f_valid = false;
+
+  // profiling
+  bool profiling = false;
+  std::vector<gpry::EventPair> pending;
+  std::vector<cudaEvent_t> pool;
+  double t_ms[gpry::T_NCATS] = {0, 0, 0, 0, 0, 0};
+  double n_launches = 0, n_contract_launches = 0;
+};
+
+namespace gpry {
+
+// RAII timing scope: records an event pair on `s` when profiling is on; counts launches.
+struct TimedScope {
+  gpry_state* st;
+  cudaStream_t s;
+  int cat;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  TimedScope(gpry_state* st_, cudaStream_t s_, int cat_, int launches = 1);
+  ~TimedScope();
+};
+void resolve_timings(gpry_state* st);
+
+// predict.cu
+void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mean,
+                      bool want_var, bool want_acq, double zeta, double sigma_n, double y_max,
+                      double* d_mean, double* d_std, double* d_acq, cudaStream_t s);
+void mean_grad_device(gpry_state* st, const double* x_host, double* out_host);
+void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_t,
+                  const double* alpha_, const double* V_host, const double* V_dev_rowmajor,
+                  const double* VT_dev_rowmajor, const double* alpha_dev, double c,
+                  const double* ell, const double* x_min, const double* x_width, double y_mean,
+                  double y_std, double clip_hi);
+// topk.cu
+int64_t topk_device(gpry_state* st, const double* d_scores, int64_t M, int Kp, int64_t idx_base,
+                    double** d_keys_out, int64_t** d_idx_out, cudaStream_t s);
+void gather_topk(gpry_state* st, const int64_t* d_idx, int64_t n, int64_t idx_base,
+                 const double* dX, int d, const double* d_mean, const double* d_std,
+                 double* o_mean, double* o_std, double* o_X, cudaStream_t s);
+// train.cu
+void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,
+                      const double* noise2, const double* y_t, const double* theta,
+                      double* out_L, double* out_V, double* out_alpha, double* out_logdet_half,
+                      int* info, bool keep);
+void lml_batched_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,
+                        const double* noise2, const double* y_t, const double* thetas, int B,
+                        double* out_lml, double* out_grad, int* out_info);
+
+}  // namespace gpry

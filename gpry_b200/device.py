@@ -1,0 +1,228 @@
+"""
+``DeviceGP``: one GP model resident on one B200, driven through the C ABI.
+
+This is the thin layer between the reference-shaped Python classes (``gpry_b200.gpr``,
+``gpry_b200.gp_acquisition``) and ``libgpry_b200.so``.  Inputs / outputs are numpy arrays
+(host path: the library does the H2D / D2H copies) or torch CUDA tensors (device path: raw
+device pointers are handed over, nothing is copied).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KERNEL_KINDS, MAX_TOPK, check, as_f64, ptr
+
+
+def _is_torch_cuda(a):
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        return None
+    if isinstance(stream, int):
+        return C.c_void_p(stream)
+    return C.c_void_p(stream.cuda_stream)  # torch.cuda.Stream
+
+
+class DeviceGP:
+    """Opaque device state + the hot-path calls.  Not picklable by design: the owning
+    ``GaussianProcessRegressor`` keeps it outside of its pickled/deep-copied attributes and
+    rebuilds it lazily (SURVEY.md section 5 "Checkpoint / resume")."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load_library()
+        h = C.c_void_p()
+        check(self._lib.gpry_state_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.N = self.d = 0
+        self.kind = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gpry_state_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __reduce__(self):
+        raise TypeError("DeviceGP holds device memory and cannot be pickled")
+
+    # ------------------------------------------------------------------ model upload
+    def upload(self, kind, X_train_, alpha_, V_, c, ell, x_min=None, x_width=None,
+               y_mean=0.0, y_std=1.0, clip_hi=np.inf):
+        X_train_ = as_f64(X_train_)
+        N, d = X_train_.shape
+        alpha_ = as_f64(alpha_, (N,))
+        V_ = as_f64(V_, (N, N))
+        ell = as_f64(np.broadcast_to(ell, (d,)))
+        x_min = None if x_min is None else as_f64(x_min, (d,))
+        x_width = None if x_width is None else as_f64(x_width, (d,))
+        check(self._lib.gpry_state_upload(
+            self._h, KERNEL_KINDS[kind], N, d, ptr(X_train_), ptr(alpha_), ptr(V_), float(c),
+            ptr(ell), ptr(x_min), ptr(x_width), float(y_mean), float(y_std), float(clip_hi)))
+        self.N, self.d, self.kind = N, d, kind
+
+    def adopt_factorization(self, c, ell, x_min=None, x_width=None, y_mean=0.0, y_std=1.0,
+                            clip_hi=np.inf):
+        d = self._f_d
+        ell = as_f64(np.broadcast_to(ell, (d,)))
+        x_min = None if x_min is None else as_f64(x_min, (d,))
+        x_width = None if x_width is None else as_f64(x_width, (d,))
+        check(self._lib.gpry_state_adopt_factorization(
+            self._h, float(c), ptr(ell), ptr(x_min), ptr(x_width), float(y_mean),
+            float(y_std), float(clip_hi)))
+        self.N, self.d, self.kind = self._f_N, d, self._f_kind
+
+    # ------------------------------------------------------------------ candidate side
+    def _prep_X(self, X):
+        if _is_torch_cuda(X):
+            if X.dtype.is_floating_point and X.element_size() == 8 and X.is_contiguous():
+                return X, int(X.shape[0]), _lib.X_ON_DEVICE
+            raise ValueError("device candidates must be a contiguous float64 tensor")
+        if hasattr(X, "data_ptr"):  # torch CPU tensor (e.g. pinned): use its memory directly
+            if not (X.is_contiguous() and X.element_size() == 8):
+                raise ValueError("host tensor candidates must be contiguous float64")
+            return X, int(X.shape[0]), 0
+        X = as_f64(X)
+        if X.ndim != 2 or X.shape[1] != self.d:
+            raise ValueError(f"X must be (M, {self.d}), got {X.shape}")
+        return X, X.shape[0], 0
+
+    def predict(self, X, return_mean=True, return_std=False, stream=None, out=None):
+        """mean and/or std.  numpy in -> numpy out; torch CUDA in -> torch CUDA out."""
+        X, M, where = self._prep_X(X)
+        what = (_lib.WANT_MEAN if return_mean else 0) | (_lib.WANT_STD if return_std else 0)
+        if where & _lib.X_ON_DEVICE:
+            import torch
+            mean = torch.empty(M, dtype=torch.float64, device=X.device) if return_mean else None
+            std = torch.empty(M, dtype=torch.float64, device=X.device) if return_std else None
+            where |= _lib.OUT_ON_DEVICE
+        else:
+            mean = np.empty(M) if return_mean else None
+            std = np.empty(M) if return_std else None
+        check(self._lib.gpry_predict(self._h, ptr(X), M, what, where, ptr(mean), ptr(std),
+                                     _stream_ptr(stream)))
+        return mean, std
+
+    def predict_logexp(self, X, zeta, sigma_n, y_max, stream=None):
+        X, M, where = self._prep_X(X)
+        if where & _lib.X_ON_DEVICE:
+            import torch
+            outs = [torch.empty(M, dtype=torch.float64, device=X.device) for _ in range(3)]
+            where |= _lib.OUT_ON_DEVICE
+        else:
+            outs = [np.empty(M) for _ in range(3)]
+        check(self._lib.gpry_predict_logexp(self._h, ptr(X), M, float(zeta), float(sigma_n),
+                                            float(y_max), where, ptr(outs[0]), ptr(outs[1]),
+                                            ptr(outs[2]), _stream_ptr(stream)))
+        return tuple(outs)
+
+    def predict_logexp_topk(self, X, zeta, sigma_n, y_max, Kp, idx_offset=0, stream=None,
+                            device_out=False, want_X=True):
+        """The Kp best candidates by LogExp: (acq, idx, mean, std, X) sorted by descending
+        acq.  Only these records leave the GPU (``device_out``: they stay in torch tensors)."""
+        X, M, where = self._prep_X(X)
+        Kp = int(min(Kp, MAX_TOPK))
+        n_out = C.c_int64(0)
+        d = self.d
+        if device_out:
+            import torch
+            dev = X.device if _is_torch_cuda(X) else torch.device("cuda", self.device)
+            acq = torch.empty(Kp, dtype=torch.float64, device=dev)
+            idx = torch.empty(Kp, dtype=torch.int64, device=dev)
+            mean = torch.empty(Kp, dtype=torch.float64, device=dev)
+            std = torch.empty(Kp, dtype=torch.float64, device=dev)
+            Xo = torch.empty((Kp, d), dtype=torch.float64, device=dev) if want_X else None
+            where |= _lib.OUT_ON_DEVICE
+        else:
+            acq, mean, std = np.empty(Kp), np.empty(Kp), np.empty(Kp)
+            idx = np.empty(Kp, dtype=np.int64)
+            Xo = np.empty((Kp, d)) if want_X else None
+        check(self._lib.gpry_predict_logexp_topk(
+            self._h, ptr(X), M, float(zeta), float(sigma_n), float(y_max), Kp, int(idx_offset),
+            where, ptr(acq), ptr(idx), ptr(mean), ptr(std), ptr(Xo), C.byref(n_out),
+            _stream_ptr(stream)))
+        n = n_out.value
+        return (acq[:n], idx[:n], mean[:n], std[:n], None if Xo is None else Xo[:n])
+
+    def topk(self, scores, Kp, stream=None):
+        Kp = int(min(Kp, MAX_TOPK))
+        n_out = C.c_int64(0)
+        if _is_torch_cuda(scores):
+            import torch
+            M = scores.numel()
+            vals = torch.empty(Kp, dtype=torch.float64, device=scores.device)
+            idx = torch.empty(Kp, dtype=torch.int64, device=scores.device)
+            where = _lib.X_ON_DEVICE | _lib.OUT_ON_DEVICE
+        else:
+            scores = as_f64(scores)
+            M = scores.size
+            vals, idx, where = np.empty(Kp), np.empty(Kp, dtype=np.int64), 0
+        check(self._lib.gpry_topk(self._h, ptr(scores), M, Kp, where, ptr(vals), ptr(idx),
+                                  C.byref(n_out), _stream_ptr(stream)))
+        return vals[:n_out.value], idx[:n_out.value]
+
+    def mean_grad(self, x):
+        x = as_f64(x).reshape(-1)
+        if x.size != self.d:
+            raise ValueError(f"x must have {self.d} entries")
+        out = np.empty(self.d)
+        check(self._lib.gpry_mean_grad(self._h, ptr(x), ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ training side
+    def factorize(self, kind, X_train_, noise2, y_train_, theta, want_L=True, want_V=True,
+                  keep_on_device=False):
+        """K = k_theta(X_,X_) + diag(noise2) -> (L_, V_, alpha_, sum(log diag L), info)."""
+        X_train_ = as_f64(X_train_)
+        N, d = X_train_.shape
+        noise2 = as_f64(np.broadcast_to(noise2, (N,)))
+        y_train_ = as_f64(y_train_, (N,))
+        theta = as_f64(theta, (d + 1,))
+        L = np.empty((N, N)) if want_L else None
+        V = np.empty((N, N)) if want_V else None
+        alpha_ = np.empty(N)
+        logdet_half = C.c_double(0.0)
+        info = C.c_int(0)
+        check(self._lib.gpry_factorize(
+            self._h, KERNEL_KINDS[kind], N, d, ptr(X_train_), ptr(noise2), ptr(y_train_),
+            ptr(theta), ptr(L), ptr(V), ptr(alpha_), C.byref(logdet_half), C.byref(info),
+            1 if keep_on_device else 0))
+        if keep_on_device and info.value == 0:
+            self._f_N, self._f_d, self._f_kind = N, d, kind
+        return L, V, alpha_, logdet_half.value, info.value
+
+    def lml_batched(self, kind, X_train_, noise2, y_train_, thetas, eval_gradient=True):
+        X_train_ = as_f64(X_train_)
+        N, d = X_train_.shape
+        noise2 = as_f64(np.broadcast_to(noise2, (N,)))
+        y_train_ = as_f64(y_train_, (N,))
+        thetas = np.atleast_2d(as_f64(thetas))
+        B = thetas.shape[0]
+        if thetas.shape[1] != d + 1:
+            raise ValueError(f"thetas must be (B, {d + 1})")
+        lml = np.empty(B)
+        grad = np.empty((B, d + 1)) if eval_gradient else None
+        info = np.zeros(B, dtype=np.int32)
+        check(self._lib.gpry_lml_batched(
+            self._h, KERNEL_KINDS[kind], N, d, ptr(X_train_), ptr(noise2), ptr(y_train_),
+            ptr(thetas), B, ptr(lml), ptr(grad), ptr(info)))
+        return lml, grad, info
+
+    # ------------------------------------------------------------------ profiling
+    def set_profiling(self, enable=True):
+        check(self._lib.gpry_set_profiling(self._h, 1 if enable else 0))
+
+    def timings(self, reset=True):
+        out = np.zeros(8)
+        check(self._lib.gpry_get_timings(self._h, ptr(out), 1 if reset else 0))
+        keys = ["build_ms", "contract_ms", "finish_ms", "topk_ms", "h2d_ms", "d2h_ms",
+                "launches", "contract_launches"]
+        return dict(zip(keys, out.tolist()))

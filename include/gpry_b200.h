@@ -1,0 +1,169 @@
+/*
+ * gpry_b200 -- C ABI of the B200-native GP surrogate hot path (drop-in boundary).
+ *
+ * One shared library (gpry_b200/libgpry_b200.so, built by __graft_entry__.build()) exports
+ * the entry points below.  Plain C: opaque handle, raw pointers, sizes, int status codes.
+ * No torch types.  Every pointer argument may be a HOST pointer or a DEVICE pointer on the
+ * state's GPU, as told by the GPRY_*_ON_DEVICE bits of `where`.  All floating point is
+ * IEEE binary64; indices are int64.  All calls are synchronous with respect to the host
+ * unless stated; they enqueue work on `stream` (a cudaStream_t passed as void*, NULL = the
+ * legacy default stream) and, for host outputs, synchronize that stream before returning.
+ *
+ * Each entry point replaces a piece of the reference GPry 3.0.0 (Python; file:line are
+ * into the reference tree, "sklearn:" into scikit-learn 1.9.0 gaussian_process/):
+ *
+ *   gpry_state_upload        state produced by GaussianProcessRegressor._update_model /
+ *                            _kernel_inverse (gpr.py:996-1020, 1453-1465): X_train_, alpha_,
+ *                            V_ = L^-1, kernel_ hyper-parameters, Normalize_bounds /
+ *                            Normalize_y scalars (preprocessing.py:380, 620, 630)
+ *   gpry_predict             GaussianProcessRegressor.predict(return_std) and predict_std
+ *                            arithmetic, gpr.py:1176-1227, 1325-1347 (kernel call
+ *                            sklearn:kernels.py:971,1278,1569-1570,1720-1729)
+ *   gpry_predict_logexp      the above + LogExp.f, acquisition_functions.py:1068-1074, as
+ *                            evaluated by NORA (mpi.py:182-218 compute_y_parallel,
+ *                            gp_acquisition.py:1049-1051, 1110-1125)
+ *   gpry_predict_logexp_topk the above + the descending-acquisition pre-ranking that
+ *                            RankedPool.add(method="single sort acq") starts from
+ *                            (gp_acquisition.py:1326-1333); only the K' best leave the GPU
+ *   gpry_mean_grad           predict(return_mean_grad) for one point, gpr.py:1236-1242 with
+ *                            Kernel.gradient_x kernels.py:257-278, 363-432, 687-699
+ *   gpry_factorize           _update_model + _kernel_inverse: K = k(X_,X_) + diag(alpha),
+ *                            L_ = chol(K), V_ = L^-1, alpha_ = K^-1 y_  (gpr.py:1015-1017,
+ *                            1456-1465)
+ *   gpry_lml_batched         log_marginal_likelihood(theta, eval_gradient) for a batch of
+ *                            theta, gpr.py:876-881 -> sklearn:_gpr.py:541-656 with kernel
+ *                            gradients sklearn:kernels.py:964-969, 1283-1292, 1581-1584,
+ *                            1752-1771
+ *
+ * Return value: 0 on success; GPRY_ERR_* (<0) on failure, message via gpry_last_error().
+ * Non-positive-definite matrices are reported through `info` outputs (LAPACK convention:
+ * info = k > 0 means the leading minor of order k is not positive definite), never as an
+ * error code: the Python layer turns them into numpy.linalg.LinAlgError (gpr.py:1458-1464)
+ * or into (-inf, 0) (sklearn:_gpr.py:592-593).
+ */
+#ifndef GPRY_B200_H
+#define GPRY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPRY_ABI_VERSION 1
+
+/* kernel kinds: ConstantKernel * {RBF, Matern(nu=1.5), Matern(nu=2.5)}, anisotropic */
+#define GPRY_KERNEL_RBF 0
+#define GPRY_KERNEL_MATERN15 1
+#define GPRY_KERNEL_MATERN25 2
+
+/* `where` bits */
+#define GPRY_X_ON_DEVICE 1   /* input candidates are a device pointer   */
+#define GPRY_OUT_ON_DEVICE 2 /* output arrays are device pointers       */
+
+/* `what` bits for gpry_predict */
+#define GPRY_WANT_MEAN 1
+#define GPRY_WANT_STD 2
+
+#define GPRY_OK 0
+#define GPRY_ERR_CUDA -1
+#define GPRY_ERR_ARG -2
+#define GPRY_ERR_STATE -3 /* state has no uploaded model */
+#define GPRY_ERR_NOMEM -4
+
+typedef struct gpry_state gpry_state;
+
+int gpry_abi_version(void);
+const char* gpry_last_error(void);
+
+/* Number of CUDA devices visible; <0 on error. */
+int gpry_device_count(void);
+
+int gpry_state_create(int device, gpry_state** out);
+int gpry_state_destroy(gpry_state* st);
+
+/*
+ * Upload a fitted model.  X_train_t is the TRANSFORMED training set (N x d, row major),
+ * alpha_ (N), V (N x N row major, lower triangular = L^-1; the strict upper triangle is
+ * ignored).  c = constant_value, ell[d] = length scales.  Candidates are transformed on the
+ * device as ((x - x_min) / x_width) / ell  (identity: x_min = 0, x_width = 1).  Outputs are
+ * de-normalised as mean * y_std + y_mean, std * y_std (identity: 0, 1) and the mean is
+ * clipped above at clip_hi (+inf = no clipping).  All pointers are host pointers.
+ */
+int gpry_state_upload(gpry_state* st, int kind, int N, int d, const double* X_train_t,
+                      const double* alpha_, const double* V, double c, const double* ell,
+                      const double* x_min, const double* x_width, double y_mean,
+                      double y_std, double clip_hi);
+
+/* Same, but V / alpha_ are taken from the device-resident result of the last
+ * gpry_factorize(..., keep_on_device=1) on this state (no N^2 host round trip). */
+int gpry_state_adopt_factorization(gpry_state* st, double c, const double* ell,
+                                   const double* x_min, const double* x_width,
+                                   double y_mean, double y_std, double clip_hi);
+
+/* Query what is loaded: N, d, kind (any may be NULL). Returns GPRY_ERR_STATE if empty. */
+int gpry_state_info(const gpry_state* st, int* N, int* d, int* kind);
+
+/* Posterior mean and/or std at M candidates X (M x d row major, un-transformed). */
+int gpry_predict(gpry_state* st, const double* X, int64_t M, int what, int where,
+                 double* out_mean, double* out_std, void* stream);
+
+/* mean, std and acq = 2 zeta (mean - y_max) + log(sqrt(max(std^2 - sigma_n^2, 0))).
+ * Any of the three outputs may be NULL. */
+int gpry_predict_logexp(gpry_state* st, const double* X, int64_t M, double zeta,
+                        double sigma_n, double y_max, int where, double* out_mean,
+                        double* out_std, double* out_acq, void* stream);
+
+/*
+ * Fused scoring + ranking: the Kp candidates with the largest acquisition value, sorted by
+ * descending acq (ties: ascending index; NaN ranks last).  idx are positions in X plus
+ * idx_offset (so that shards report global indices).  out_X (Kp x d) may be NULL.
+ * *n_out = min(Kp, M).  Output arrays are host or device per GPRY_OUT_ON_DEVICE and must
+ * hold Kp entries; n_out is always a host pointer.
+ */
+int gpry_predict_logexp_topk(gpry_state* st, const double* X, int64_t M, double zeta,
+                             double sigma_n, double y_max, int Kp, int64_t idx_offset,
+                             int where, double* out_acq, int64_t* out_idx,
+                             double* out_mean, double* out_std, double* out_X,
+                             int64_t* n_out, void* stream);
+
+/* Top-Kp of an arbitrary device/host score array (used to merge shard results). */
+int gpry_topk(gpry_state* st, const double* scores, int64_t M, int Kp, int where,
+              double* out_scores, int64_t* out_idx, int64_t* n_out, void* stream);
+
+/* d mean / d x_ at ONE un-transformed point x (d) -> out_grad (d), host pointers. The
+ * gradient is w.r.t. the transformed coordinate, scaled by y_std (gpr.py:1237-1242). */
+int gpry_mean_grad(gpry_state* st, const double* x, double* out_grad);
+
+/*
+ * K = k_theta(X_, X_) + diag(noise2); L = chol(K); V = L^-1; alpha_ = K^-1 y_.
+ * theta = [log c, log ell_1..ell_d].  Host pointers; out_L / out_V (N x N row major, lower,
+ * upper triangle zeroed) and out_alpha (N) may be NULL.  *info = 0 or the order of the
+ * first non-positive leading minor.  If keep_on_device != 0 the factor stays resident in
+ * `st` for gpry_state_adopt_factorization.  out_logdet_half = sum(log(diag L)).
+ */
+int gpry_factorize(gpry_state* st, int kind, int N, int d, const double* X_train_t,
+                   const double* noise2, const double* y_t, const double* theta,
+                   double* out_L, double* out_V, double* out_alpha,
+                   double* out_logdet_half, int* info, int keep_on_device);
+
+/*
+ * Log marginal likelihood (and its gradient w.r.t. theta if out_grad != NULL) for B
+ * hyper-parameter vectors thetas (B x (1+d)).  out_lml (B), out_grad (B x (1+d)),
+ * out_info (B; >0 = not positive definite: lml = -inf, grad = 0).  Host pointers.
+ */
+int gpry_lml_batched(gpry_state* st, int kind, int N, int d, const double* X_train_t,
+                     const double* noise2, const double* y_t, const double* thetas, int B,
+                     double* out_lml, double* out_grad, int* out_info);
+
+/* Device timings (ms, CUDA events on the launching stream) accumulated since the last
+ * reset, per stage: [0] kstar build, [1] variance contraction, [2] finish/acquisition,
+ * [3] top-k, [4] h2d, [5] d2h, [6] kernel launches counted, [7] contraction launches.
+ * Enable with gpry_set_profiling(st, 1): adds event records around every launch. */
+int gpry_set_profiling(gpry_state* st, int enable);
+int gpry_get_timings(gpry_state* st, double* out8, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPRY_B200_H */
