@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""
+bench.py -- GP predict + LogExp + ranked-pool pre-selection throughput (candidates / s).
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): N_train = 2000, d = 12,
+ConstantKernel x RBF at fixed theta, 12.5e6 synthetic candidates PER GPU (weak scaling:
+8 GPUs -> 10^8), K' = 1024 survivors per GPU merged through an NCCL all-gather.
+
+One step = one pass of the hot path over the rank's candidate pool:
+    K* build -> variance contraction (FP64 DMMA) -> finish/LogExp -> top-K' -> all-gather+merge.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA, sm_100a)
+  python bench.py --impl reference ...                         reference arm: the CPU port of
+                                                               GPry's own path (oracle/), host cores
+Prints ONE JSON line (see README / DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gp_predict_logexp_candidates_per_sec"
+UNIT = "candidates/s"
+FP64_DGEMM_FALLBACK_TFLOPS = 35.4   # cublasDgemm 8192^3 on this pool (profiles/r01_fp64_peaks.txt)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--ntrain", type=int, default=2000)
+    p.add_argument("--dim", type=int, default=12)
+    p.add_argument("--pool", type=int, default=12_500_000, help="candidates per GPU")
+    p.add_argument("--kp", type=int, default=1024, help="survivors per GPU (K')")
+    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--cpu-chunk", type=int, default=20000)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic workload; identical for both arms
+# ------------------------------------------------------------------------------------------
+def synthetic_problem(N, d, seed=1234):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(size=(N, d))
+    y = -0.5 * np.sum(((X - 0.5) / 0.15) ** 2, axis=1)
+    ell = 0.5 if d <= 8 else (1.0 if d <= 16 else 1.5)
+    theta = np.log(np.concatenate([[1.0], np.full(d, ell)]))
+    bounds = np.array([[0.0, 1.0]] * d)
+    return X, y, theta, bounds
+
+
+def candidates_host(M, d, seed):
+    return np.random.default_rng(seed).uniform(size=(M, d))
+
+
+def cpu_thread_info():
+    try:
+        from threadpoolctl import threadpool_info
+        blas = [i for i in threadpool_info() if i.get("user_api") == "blas"]
+        n = max([i.get("num_threads", 1) for i in blas] or [os.cpu_count()])
+        return int(n), ",".join(sorted({str(i.get("internal_api")) for i in blas}))
+    except Exception:
+        return os.cpu_count(), "unknown"
+
+
+def time_cpu_port(N, d, chunk, budget_s, max_chunks=16):
+    """Times the CPU port of the reference path (oracle/gp_oracle.py: cdist + exp + dtrmm +
+    einsum, all host cores through BLAS) on a bounded sample of the same workload."""
+    from oracle import gp_oracle as orc
+    X, y, theta, bounds = synthetic_problem(N, d)
+    st = orc.GPState("rbf", theta, X, y, bounds=bounds)
+    Xc = candidates_host(chunk, d, 4321)
+    orc.predict_logexp(st, Xc[:2000])   # warm-up
+    t_used, n_done, best = 0.0, 0, None
+    while t_used < budget_s and n_done < max_chunks:
+        t0 = time.perf_counter()
+        out = orc.predict_logexp(st, Xc)
+        dt = time.perf_counter() - t0
+        t_used += dt
+        n_done += 1
+        best = dt if best is None else min(best, dt)
+    return chunk * n_done / t_used, chunk / best, n_done, st, Xc, out
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import gp_oracle as orc
+    N, d = args.ntrain, args.dim
+    X, y, theta, bounds = synthetic_problem(N, d)
+    st = orc.GPState("rbf", theta, X, y, bounds=bounds)
+    sample = 2 * args.cpu_chunk
+    Xc = candidates_host(sample, d, 4321)
+
+    def step():
+        for i in range(0, sample, args.cpu_chunk):
+            orc.predict_logexp(st, Xc[i:i + args.cpu_chunk])
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    cores, blas = cpu_thread_info()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"GP predict+LogExp N_train={N} d={d} RBF, CPU port of the "
+                               "reference path (cdist+exp+dtrmm+einsum)",
+                   "sample_candidates_per_step": sample, "chunk": args.cpu_chunk},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} candidates/step in chunks of {args.cpu_chunk}, "
+                                   f"BLAS={blas}, os.cpu_count={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])), mx.append(float(parts[1])), pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                       power_w_max=float(max(pw)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def fit_state_for_bench(dev, N, d):
+    """Training state for the synthetic problem: Normalize_bounds / Normalize_y scalars on the
+    host (O(N)), kernel matrix + Cholesky + L^-1 + alpha on the GPU (gpry_factorize)."""
+    X, y, theta, bounds = synthetic_problem(N, d)
+    y_mean, y_std = float(np.mean(y)), float(np.std(y))
+    noise_level = 1e-2
+    X_ = (X - bounds[:, 0]) / (bounds[:, 1] - bounds[:, 0])
+    y_ = (y - y_mean) / y_std
+    noise2 = np.full(N, (noise_level / y_std) ** 2)
+    L, V, alpha_, _, info = dev.factorize("rbf", X_, noise2, y_, theta, want_L=False)
+    assert info == 0, "synthetic kernel matrix not positive definite"
+    clip_hi = 1.1 * y.max() - 0.1 * y.min()
+    model = dict(kind="rbf", X_=X_, alpha_=alpha_, V=V, c=float(np.exp(theta[0])),
+                 ell=np.exp(theta[1:]), x_min=bounds[:, 0], x_width=bounds[:, 1] - bounds[:, 0],
+                 y_mean=y_mean, y_std=y_std, clip_hi=clip_hi, y_max=float(y.max()),
+                 noise_level=noise_level, zeta=float(d) ** -0.85)
+    return model
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gpry_b200 import DeviceGP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev_t = torch.device("cuda", local)
+    N, d, M, Kp = args.ntrain, args.dim, args.pool, args.kp
+    dev = DeviceGP(local)
+
+    # ---- model: fitted on rank 0, broadcast once (per refit), uploaded on every GPU ----
+    if rank == 0:
+        model = fit_state_for_bench(dev, N, d)
+    t_bcast_ms = 0.0
+    if world > 1:
+        meta = [model if rank == 0 else None]
+        big = {}
+        if rank == 0:
+            big = {k: torch.from_numpy(np.ascontiguousarray(model[k])).to(dev_t)
+                   for k in ("X_", "alpha_", "V")}
+            meta = [{k: v for k, v in model.items() if k not in big}]
+        dist.broadcast_object_list(meta, src=0)
+        if rank != 0:
+            model = meta[0]
+            big = {"X_": torch.empty((N, d), dtype=torch.float64, device=dev_t),
+                   "alpha_": torch.empty(N, dtype=torch.float64, device=dev_t),
+                   "V": torch.empty((N, N), dtype=torch.float64, device=dev_t)}
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in ("X_", "alpha_", "V"):
+            dist.broadcast(big[k], src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        t_bcast_ms = e0.elapsed_time(e1)
+        if rank != 0:
+            for k in big:
+                model[k] = big[k].cpu().numpy()
+    dev.upload(model["kind"], model["X_"], model["alpha_"], model["V"], model["c"], model["ell"],
+               model["x_min"], model["x_width"], model["y_mean"], model["y_std"],
+               model["clip_hi"])
+    zeta, sig, ymax = model["zeta"], model["noise_level"], model["y_max"]
+
+    # ---- candidates: this rank's shard, generated on the device (Philox), resident in HBM ----
+    gen = torch.Generator(device=dev_t)
+    gen.manual_seed(4321 + rank)
+    Xd = torch.rand((M, d), dtype=torch.float64, device=dev_t, generator=gen)
+    idx_offset = rank * M
+    stream = torch.cuda.current_stream()
+
+    def merge(acq, idx):
+        """All-gather of the per-GPU survivor lists + final top-K' (every rank ends with the
+        same merged list, as after gp_acquisition.py:1190 bcast)."""
+        if world == 1:
+            return acq, idx
+        ga = torch.empty(world * Kp, dtype=torch.float64, device=dev_t)
+        gi = torch.empty(world * Kp, dtype=torch.int64, device=dev_t)
+        dist.all_gather_into_tensor(ga, acq.contiguous())
+        dist.all_gather_into_tensor(gi, idx.contiguous())
+        vals, pos = dev.topk(ga, Kp, stream=stream)
+        return vals, gi[pos]
+
+    def step():
+        acq, idx, mean, std, _ = dev.predict_logexp_topk(
+            Xd, zeta, sig, ymax, Kp, idx_offset=idx_offset, stream=stream, device_out=True,
+            want_X=False)
+        return merge(acq, idx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    dev.set_profiling(True)
+    dev.timings(reset=True)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        top_acq, top_idx = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if clocks else {}
+    tm = dev.timings(reset=True)
+    dev.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev_t)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * M * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers (pinned) ----
+    e2e = None
+    if not args.no_e2e:
+        Xh = torch.empty((M, d), dtype=torch.float64, pin_memory=True)
+        Xh.copy_(Xd)
+
+        def step_e2e():
+            acq, idx, mean, std, Xo = dev.predict_logexp_topk(
+                Xh, zeta, sig, ymax, Kp, idx_offset=idx_offset, stream=stream)
+            if world > 1:
+                a, i = merge(torch.from_numpy(acq).to(dev_t), torch.from_numpy(idx).to(dev_t))
+                return a.cpu().numpy(), i.cpu().numpy()
+            return acq, idx
+
+        step_e2e()
+        barrier()
+        e0.record()
+        for _ in range(args.e2e_steps):
+            step_e2e()
+        e1.record()
+        barrier()
+        ms2 = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms2], dtype=torch.float64, device=dev_t)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t.item())
+        e2e = {"value": world * M * args.e2e_steps / (ms2 * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": world * M * d * 8,
+               "d2h_bytes_per_step": world * Kp * (4 + d) * 8,
+               "ms_per_step": ms2 / args.e2e_steps}
+        del Xh
+
+    # ---- roofline of the dominant kernel (variance contraction, FP64 tensor pipe) ----
+    n_launch = max(tm["contract_launches"], 1.0)
+    cands_per_launch = M * args.steps / n_launch
+    flop_per_cand = N * (N + 1) + 2 * N          # V k* (lower tri.) + sum of squares
+    contract_ms_per_launch = tm["contract_ms"] / n_launch
+    achieved = flop_per_cand * cands_per_launch / (contract_ms_per_launch * 1e-3) * 1e-12
+    peak, peak_src = FP64_DGEMM_FALLBACK_TFLOPS, "cublasDgemm 8192^3, profiles/r01_fp64_peaks.txt"
+    try:   # measure the FP64 tensor peak live (MEASURED_PEAKS.json has no FP64 entry)
+        a = torch.randn(8192, 8192, dtype=torch.float64, device=dev_t)
+        b = torch.randn(8192, 8192, dtype=torch.float64, device=dev_t)
+        (a @ b)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            e0.record()
+            (a @ b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        peak, peak_src = 2 * 8192 ** 3 / best * 1e-9, "cublasDgemm 8192^3 measured in this run"
+        del a, b
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "var_contract_kernel (FP64 DMMA.8x8x4)",
+                "flop_per_candidate": flop_per_cand,
+                "ms_per_launch": contract_ms_per_launch,
+                "stage_ms_per_step": {k: tm[k] / args.steps for k in
+                                      ("build_ms", "contract_ms", "finish_ms", "topk_ms")}}
+
+    # ---- agreement check + CPU baseline (rank 0, N = 1 run only for the baseline) ----
+    agreement, cpu_baseline = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        thr, thr_best, n_chunks, st, Xc, (mo, so, ao) = time_cpu_port(
+            N, d, args.cpu_chunk, args.cpu_seconds)
+        mg, sg, ag = dev.predict_logexp(Xc, zeta, sig, ymax)
+        ok = np.isfinite(ao) & (so ** 2 - sig ** 2 > 1e-6 * st.y_std ** 2)
+        agreement = {
+            "n": int(len(Xc)),
+            "mean_err": float(np.max(np.abs(mg - mo)) / st.y_std),
+            "var_err": float(np.max(np.abs(sg ** 2 - so ** 2)) / st.y_std ** 2),
+            "acq_err": float(np.max(np.abs(ag[ok] - ao[ok]))),
+            "tolerance": 1e-10,
+        }
+        # ranked list vs an independent sort of the same device scores
+        acq_full = dev.predict_logexp(Xd, zeta, sig, ymax, stream=stream)[2]
+        ref_vals, ref_idx = torch.sort(acq_full, descending=True, stable=True)
+        a1, i1, _, _, _ = dev.predict_logexp_topk(Xd, zeta, sig, ymax, Kp, stream=stream,
+                                                  device_out=True, want_X=False)
+        agreement["topk_identical"] = bool(torch.equal(i1, ref_idx[:Kp]))
+        agreement["verified"] = bool(agreement["mean_err"] < 1e-10
+                                     and agreement["var_err"] < 1e-10
+                                     and agreement["topk_identical"])
+        cores, blas = cpu_thread_info()
+        cpu_baseline = {"value": thr, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{n_chunks} x {args.cpu_chunk} candidates of the same workload "
+                                  f"(N_train={N}, d={d}); best chunk {thr_best:.0f} cand/s; "
+                                  f"BLAS={blas}; os.cpu_count={os.cpu_count()}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"NORA ranked-pool scoring: predict mean+std + LogExp + "
+                                   f"top-{Kp}, N_train={N}, d={d}, RBF, {M} candidates/GPU",
+                       "candidates_per_gpu": M, "candidates_total": world * M, "n_train": N,
+                       "dim": d, "kprime": Kp, "parallelism": f"candidate-sharded x{world}",
+                       "l2": "inputs (1.2 GB/GPU) and K* scratch (>600 MB) exceed the 126 MB L2",
+                       "state_bcast_ms": t_bcast_ms},
+            "e2e": e2e, "gpu_launches": int(tm["launches"]), "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "agreement": agreement, "clocks": clk,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    dev.close()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

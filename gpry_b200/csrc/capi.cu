@@ -130,7 +130,7 @@ int gpry_state_upload(gpry_state* st, int kind, int N, int d, const double* X_tr
                       double clip_hi) {
   return guarded([&] {
     GPRY_CHECK_ARG(st && X_train_t && alpha_ && V && ell, "NULL argument");
-    upload_model(st, kind, N, d, X_train_t, alpha_, V, nullptr, nullptr, nullptr, c, ell, x_min,
+    upload_model(st, kind, N, d, X_train_t, alpha_, V, nullptr, nullptr, 0, nullptr, c, ell, x_min,
                  x_width, y_mean, y_std, clip_hi);
   });
 }
@@ -143,10 +143,12 @@ int gpry_state_adopt_factorization(gpry_state* st, double c, const double* ell,
     if (!st->f_valid)
       throw GpryError{GPRY_ERR_STATE, "no device-resident factorization to adopt"};
     const int N = st->f_N, d = st->f_d;
+    const int Np = round_up(N, TILE_ROWS);
     std::vector<double> Xt((size_t)N * d);
-    GPRY_CUDA(cudaMemcpy(Xt.data(), st->f_vec.p + 4 * (size_t)N, (size_t)N * d * 8,
+    // train.cu layout of f_vec: [alpha Np][t Np][y Np][noise2 Np][X_ N*d]...
+    GPRY_CUDA(cudaMemcpy(Xt.data(), st->f_vec.p + 4 * (size_t)Np, (size_t)N * d * 8,
                          cudaMemcpyDeviceToHost));
-    upload_model(st, st->f_kind, N, d, Xt.data(), nullptr, nullptr, nullptr, st->f_VT.p,
+    upload_model(st, st->f_kind, N, d, Xt.data(), nullptr, nullptr, nullptr, st->f_VT.p, Np,
                  st->f_vec.p /* alpha_ */, c, ell, x_min, x_width, y_mean, y_std, clip_hi);
   });
 }

@@ -468,7 +468,7 @@ __global__ void pad_copy_kernel(const double* __restrict__ src, int n, int npad,
 
 void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                   const double* alpha_, const double* V_host, const double* V_dev_rowmajor,
-                  const double* VT_dev_rowmajor, const double* alpha_dev, double c,
+                  const double* VT_dev_rowmajor, int ldV, const double* alpha_dev, double c,
                   const double* ell, const double* x_min, const double* x_width, double y_mean,
                   double y_std, double clip_hi) {
   GPRY_CHECK_ARG(kind >= 0 && kind <= 2, "unknown kernel kind");
@@ -524,10 +524,12 @@ void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_
   }
   const double* Vsrc = V_dev_rowmajor;
   int transposed = 0;
+  if (ldV <= 0) ldV = N;
   if (V_host) {
     st->tmp.reserve((size_t)N * N);
     GPRY_CUDA(cudaMemcpyAsync(st->tmp.p, V_host, (size_t)N * N * 8, cudaMemcpyHostToDevice, s));
     Vsrc = st->tmp.p;
+    ldV = N;
   } else if (VT_dev_rowmajor) {
     Vsrc = VT_dev_rowmajor;
     transposed = 1;
@@ -535,7 +537,7 @@ void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_
   GPRY_CHECK_ARG(Vsrc != nullptr, "no V given");
   int64_t total = vtile_count(st->nJ) * TILE_DOUBLES;
   st->Vt.reserve((size_t)total);
-  pack_v_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Vsrc, N, N, transposed, st->nJ,
+  pack_v_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Vsrc, N, ldV, transposed, st->nJ,
                                                                st->Vt.p);
   GPRY_CUDA(cudaGetLastError());
   GPRY_CUDA(cudaStreamSynchronize(s));

@@ -120,7 +120,7 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
 void mean_grad_device(gpry_state* st, const double* x_host, double* out_host);
 void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                   const double* alpha_, const double* V_host, const double* V_dev_rowmajor,
-                  const double* VT_dev_rowmajor, const double* alpha_dev, double c,
+                  const double* VT_dev_rowmajor, int ldV, const double* alpha_dev, double c,
                   const double* ell, const double* x_min, const double* x_width, double y_mean,
                   double y_std, double clip_hi);
 // topk.cu
