@@ -119,7 +119,14 @@ int gpry_state_destroy(gpry_state* st) {
     st->Xdev.release(); st->o_mean.release(); st->o_std.release(); st->o_acq.release();
     for (int b = 0; b < 2; b++) { st->tk_keys[b].release(); st->tk_idx[b].release(); }
     st->tmp.release(); st->small.release();
-    st->f_K.release(); st->f_VT.release(); st->f_W.release(); st->f_vec.release();
+    for (auto* ts : st->f_sets) {
+      ts->K.release(); ts->VT.release(); ts->W.release(); ts->vec.release();
+      if (ts->stream) cudaStreamDestroy(ts->stream);
+      delete ts;
+    }
+    st->f_prob.release();
+    if (st->f_pinned) cudaFreeHost(st->f_pinned);
+    if (st->f_evt) cudaEventDestroy(st->f_evt);
     delete st;
   });
 }
@@ -145,11 +152,12 @@ int gpry_state_adopt_factorization(gpry_state* st, double c, const double* ell,
     const int N = st->f_N, d = st->f_d;
     const int Np = round_up(N, TILE_ROWS);
     std::vector<double> Xt((size_t)N * d);
-    // train.cu layout of f_vec: [alpha Np][t Np][y Np][noise2 Np][X_ N*d]...
-    GPRY_CUDA(cudaMemcpy(Xt.data(), st->f_vec.p + 4 * (size_t)Np, (size_t)N * d * 8,
+    // train.cu layouts: f_prob = [y Np][noise2 Np][X_ N*d]; set 0: VT, vec = [alpha Np]...
+    GPRY_CUDA(cudaMemcpy(Xt.data(), st->f_prob.p + 2 * (size_t)Np, (size_t)N * d * 8,
                          cudaMemcpyDeviceToHost));
-    upload_model(st, st->f_kind, N, d, Xt.data(), nullptr, nullptr, nullptr, st->f_VT.p, Np,
-                 st->f_vec.p /* alpha_ */, c, ell, x_min, x_width, y_mean, y_std, clip_hi);
+    upload_model(st, st->f_kind, N, d, Xt.data(), nullptr, nullptr, nullptr, st->f_sets[0]->VT.p,
+                 Np, st->f_sets[0]->vec.p /* alpha_ */, c, ell, x_min, x_width, y_mean, y_std,
+                 clip_hi);
   });
 }
 

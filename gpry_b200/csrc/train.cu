@@ -11,7 +11,8 @@
 // L, L^-1, alpha and log det untouched.
 //
 //   kmat_kernel        K = c g(r) + diag(noise2)                       (lower tiles)
-//   potf2_inv_kernel   128 x 128 diagonal block: L_jj and W_jj = L_jj^-1     (one CTA)
+//   potf2_inv_kernel   128 x 128 diagonal block: L_jj and W_jj = L_jj^-1 (one CTA: 32 x 32
+//                      sub-blocks factored in registers by one warp, 32^3 products on DMMA)
 //   gemm_nt_kernel     C (+)= alpha A B^T on FP64 tensor cores (DMMA.8x8x4), cp.async
 //                      4-stage pipeline; used for the panel solve (x W_jj^T), the SYRK
 //                      trailing update, the right-looking sweep that builds V^T = L^-T and
@@ -82,75 +83,179 @@ kmat_kernel(const double* __restrict__ T, int N, int d, int Np, double c,
 }
 
 // ---------------------------------------------------------------------------------------
-// diagonal block: Cholesky (left-looking dot-product form) + triangular inverse
-//   A: pointer to the 128 x 128 diagonal block (leading dimension ld), overwritten by L_jj
-//      (strict upper triangle zeroed); W: dense 128 x 128 = L_jj^-1 (upper zeroed).
-//   info: first failing global pivot index + 1 (0 = ok).  One CTA of 128 threads.
+// diagonal block: 128 x 128 Cholesky + triangular inverse in ONE CTA (8 warps).
+//   A: the diagonal block (leading dimension ld), overwritten by L_jj (upper triangle zeroed)
+//   W: dense 128 x 128 = L_jj^-1 (upper zeroed)
+//   info: first failing global pivot index + 1 (0 = ok)
+// The block is split in 4 x 4 sub-blocks of 32 x 32 held in shared memory ([32][36] padded,
+// conflict-free for the DMMA fragment loads).  A 32 x 32 diagonal sub-block is factored and
+// inverted by one warp entirely in registers (lane = row / column, operands exchanged with
+// warp shuffles); every 32^3 product of the blocked algorithm runs on the FP64 tensor cores,
+// one warp per product.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ int tri(int r, int c) { return r * (r + 1) / 2 + c; }
+constexpr int SB = 32;          // sub-block size
+constexpr int SBLD = 36;        // padded leading dimension (= 4 mod 16 doubles)
+constexpr int SB_DOUBLES = SB * SBLD;
+__host__ __device__ inline int sbidx(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 
-__global__ void __launch_bounds__(128)
+// acc += A (32x32, [r][k]) * op(B);  NT: B stored [n][k];  NN: B stored [k][n]
+template <bool NN>
+__device__ __forceinline__ void mm32(const double* __restrict__ A, const double* __restrict__ B,
+                                     double (&acc)[4][4][2], int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int k4 = 0; k4 < 8; k4++) {
+    double a[4], b[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) a[mi] = A[(mi * 8 + g) * SBLD + k4 * 4 + t];
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++)
+      b[ni] = NN ? B[(k4 * 4 + t) * SBLD + ni * 8 + g] : B[(ni * 8 + g) * SBLD + k4 * 4 + t];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+  }
+}
+__device__ __forceinline__ void zero_acc(double (&acc)[4][4][2]) {
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+}
+// C = beta * C + alpha * acc   (C: [32][36] in shared memory)
+__device__ __forceinline__ void store_acc(double* __restrict__ C, const double (&acc)[4][4][2],
+                                          double alpha, double beta, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+      double* c = C + (mi * 8 + g) * SBLD + ni * 8 + 2 * t;
+      if (beta != 0.0) {
+        c[0] = fma(alpha, acc[mi][ni][0], beta * c[0]);
+        c[1] = fma(alpha, acc[mi][ni][1], beta * c[1]);
+      } else {
+        c[0] = alpha * acc[mi][ni][0];
+        c[1] = alpha * acc[mi][ni][1];
+      }
+    }
+}
+
+// One warp: Cholesky of the 32 x 32 block D (lane = row, row in registers, right-looking) and
+// its inverse (lane = column, forward substitution); writes L (upper zeroed) back into D and
+// the inverse into Winv.
+__device__ __forceinline__ void factor_inv_32(double* __restrict__ D, double* __restrict__ Winv,
+                                              int lane, int pivot_offset, int* __restrict__ info) {
+  double a[SB];
+#pragma unroll
+  for (int k = 0; k < SB; k++) a[k] = D[lane * SBLD + k];
+#pragma unroll
+  for (int k = 0; k < SB; k++) {
+    double dkk = __shfl_sync(0xffffffffu, a[k], k);
+    if (!(dkk > 0.0)) {
+      if (lane == 0 && *info == 0) *info = pivot_offset + k + 1;
+      dkk = 1.0;
+    }
+    const double sq = sqrt(dkk);
+    const double lk = (lane == k) ? sq : a[k] / sq;
+    a[k] = lk;
+#pragma unroll
+    for (int j = k + 1; j < SB; j++) {
+      double ljk = __shfl_sync(0xffffffffu, lk, j);
+      if (lane >= j) a[j] = fma(-lk, ljk, a[j]);
+    }
+  }
+  // inverse: lane c holds column c of W
+  double w[SB];
+#pragma unroll
+  for (int i = 0; i < SB; i++) {
+    double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int m = 0; m < i; m++) {
+      double lim = __shfl_sync(0xffffffffu, a[m], i);
+      s = fma(-lim, w[m], s);
+    }
+    double lii = __shfl_sync(0xffffffffu, a[i], i);
+    w[i] = (i >= lane) ? s / lii : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < SB; k++) {
+    D[lane * SBLD + k] = (k <= lane) ? a[k] : 0.0;
+    Winv[k * SBLD + lane] = w[k];
+  }
+}
+
+__global__ void __launch_bounds__(256)
 potf2_inv_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int row_offset,
                  int* __restrict__ info) {
   extern __shared__ double sh[];
-  double* S = sh;                      // packed lower triangle of the block / of L
-  double* Wi = sh + 128 * 129 / 2;     // packed lower triangle of the inverse
-  const int t = threadIdx.x;
-  for (int e = t; e < 128 * 128; e += 128) {
+  double* Lb = sh;                       // 10 lower sub-blocks of the block / of L
+  double* Wb = sh + 10 * SB_DOUBLES;     // 10 lower sub-blocks of the inverse
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < 128 * 128; e += 256) {
     int r = e >> 7, cidx = e & 127;
-    if (cidx <= r) S[tri(r, cidx)] = A[(size_t)r * ld + cidx];
+    int bi = r >> 5, bj = cidx >> 5;
+    if (bj <= bi) Lb[sbidx(bi, bj) * SB_DOUBLES + (r & 31) * SBLD + (cidx & 31)] = A[(size_t)r * ld + cidx];
   }
   __syncthreads();
-  // left-looking: column k of L from the rows of the already finished columns
-  for (int k = 0; k < 128; k++) {
-    double s = 0.0;
-    if (t >= k) {   // a_tk - sum_{m<k} L_tm L_km
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      const double* ri = S + tri(t, 0);
-      const double* rk = S + tri(k, 0);
-      int m = 0;
-      for (; m + 4 <= k; m += 4) {
-        s0 = fma(ri[m], rk[m], s0);
-        s1 = fma(ri[m + 1], rk[m + 1], s1);
-        s2 = fma(ri[m + 2], rk[m + 2], s2);
-        s3 = fma(ri[m + 3], rk[m + 3], s3);
-      }
-      for (; m < k; m++) s0 = fma(ri[m], rk[m], s0);
-      s = ri[k] - ((s0 + s1) + (s2 + s3));
-    }
-    if (t == k) {
-      if (!(s > 0.0)) {
-        if (*info == 0) *info = row_offset + k + 1;
-        s = 1.0;
-      }
-      S[tri(k, k)] = sqrt(s);
+  double acc[4][4][2];
+  for (int kb = 0; kb < 4; kb++) {
+    if (warp == 0)
+      factor_inv_32(Lb + sbidx(kb, kb) * SB_DOUBLES, Wb + sbidx(kb, kb) * SB_DOUBLES, lane,
+                    row_offset + kb * SB, info);
+    __syncthreads();
+    // panel: L[ib][kb] = A[ib][kb] * W_kk^T
+    if (warp < 3 - kb) {
+      const int ib = kb + 1 + warp;
+      double* blk = Lb + sbidx(ib, kb) * SB_DOUBLES;
+      zero_acc(acc);
+      mm32<false>(blk, Wb + sbidx(kb, kb) * SB_DOUBLES, acc, lane);
+      __syncwarp();
+      store_acc(blk, acc, 1.0, 0.0, lane);
     }
     __syncthreads();
-    if (t > k) S[tri(t, k)] = s / S[tri(k, k)];
-    __syncthreads();   // row k+1 (read by everybody next) now has its entry in column k
-  }
-  // inverse W = L^-1 by forward substitution; thread t owns column t, rows advance together
-  for (int i = 0; i < 128; i++) {
-    if (t <= i) {
-      const double* ri = S + tri(i, 0);
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int m = t;
-      for (; m + 4 <= i; m += 4) {
-        s0 = fma(ri[m], Wi[tri(m, t)], s0);
-        s1 = fma(ri[m + 1], Wi[tri(m + 1, t)], s1);
-        s2 = fma(ri[m + 2], Wi[tri(m + 2, t)], s2);
-        s3 = fma(ri[m + 3], Wi[tri(m + 3, t)], s3);
-      }
-      for (; m < i; m++) s0 = fma(ri[m], Wi[tri(m, t)], s0);
-      double rhs = (i == t) ? 1.0 : 0.0;
-      Wi[tri(i, t)] = (rhs - ((s0 + s1) + (s2 + s3))) / ri[i];
+    // trailing: A[ib][jb] -= L[ib][kb] * L[jb][kb]^T,  kb < jb <= ib
+    {
+      int p = 0;
+      for (int ib = kb + 1; ib < 4; ib++)
+        for (int jb = kb + 1; jb <= ib; jb++, p++)
+          if (p == warp) {
+            zero_acc(acc);
+            mm32<false>(Lb + sbidx(ib, kb) * SB_DOUBLES, Lb + sbidx(jb, kb) * SB_DOUBLES, acc, lane);
+            store_acc(Lb + sbidx(ib, jb) * SB_DOUBLES, acc, -1.0, 1.0, lane);
+          }
     }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int e = t; e < 128 * 128; e += 128) {
+  // off-diagonal blocks of the inverse: W[i][j] = -W[i][i] * sum_{k=j}^{i-1} L[i][k] W[k][j]
+  for (int dist = 1; dist < 4; dist++) {
+    if (warp < 4 - dist) {
+      const int j = warp, i = j + dist;
+      double* out = Wb + sbidx(i, j) * SB_DOUBLES;
+      zero_acc(acc);
+      for (int k = j; k < i; k++)
+        mm32<true>(Lb + sbidx(i, k) * SB_DOUBLES, Wb + sbidx(k, j) * SB_DOUBLES, acc, lane);
+      store_acc(out, acc, 1.0, 0.0, lane);
+      __syncwarp();
+      zero_acc(acc);
+      mm32<true>(Wb + sbidx(i, i) * SB_DOUBLES, out, acc, lane);
+      __syncwarp();
+      store_acc(out, acc, -1.0, 0.0, lane);
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < 128 * 128; e += 256) {
     int r = e >> 7, cidx = e & 127;
-    A[(size_t)r * ld + cidx] = (cidx <= r) ? S[tri(r, cidx)] : 0.0;
-    W[e] = (cidx <= r) ? Wi[tri(r, cidx)] : 0.0;
+    int bi = r >> 5, bj = cidx >> 5;
+    double lv = 0.0, wv = 0.0;
+    if (bj <= bi) {
+      int o = sbidx(bi, bj) * SB_DOUBLES + (r & 31) * SBLD + (cidx & 31);
+      lv = Lb[o];
+      wv = Wb[o];
+    }
+    A[(size_t)r * ld + cidx] = lv;
+    W[e] = wv;
   }
 }
 
@@ -287,15 +392,26 @@ __global__ void scale_rows_kernel(const double* __restrict__ X, int N, int d,
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < N * d) T[e] = X[e] / ell[e % d];
 }
-// t = V y = VT^T y : thread per column i of VT, rows j <= i
-__global__ void gemv_vt_t_kernel(const double* __restrict__ VT, int Np, int N,
-                                 const double* __restrict__ y, double* __restrict__ t) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Np) return;
+// t = V y = VT^T y : CTA per 32 columns of VT, 8 row groups, rows j <= i; fixed-order sums
+__global__ void __launch_bounds__(256)
+gemv_vt_t_kernel(const double* __restrict__ VT, int Np, int N, const double* __restrict__ y,
+                 double* __restrict__ t) {
+  __shared__ double red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cx;
   double s = 0.0;
-  if (i < N)
-    for (int j = 0; j <= i; j++) s = fma(VT[(size_t)j * Np + i], y[j], s);
-  t[i] = s;
+  if (i < N) {
+    const int jmax = min(N - 1, blockIdx.x * 32 + 31);
+    for (int j = ry; j <= jmax; j += 8)
+      if (j <= i) s = fma(VT[(size_t)j * Np + i], y[j], s);
+  }
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0) {
+    double v = 0.0;
+    for (int q = 0; q < 8; q++) v += red[q][cx];
+    if (i < Np) t[i] = v;
+  }
 }
 // alpha = V^T t = VT t : warp per row j, columns i >= j
 __global__ void gemv_vt_kernel(const double* __restrict__ VT, int Np, int N,
@@ -480,31 +596,42 @@ struct TrainBuffers {
   double *Winv;               // nb x 128 x 128
   double *X, *T, *noise2, *y, *ell, *alpha, *t, *scal, *partial, *grad;
   int* info;
+  cudaStream_t stream;
 };
 
-// layout of st->f_vec: [alpha Np][t Np][y Np][noise2 Np][X N*d][T N*d][ell MAX_DIM]
-//                      [scal 8][grad MAX_DIM+8][info (as double) 2][Winv nb*128*128][partial ...]
-static TrainBuffers carve(gpry_state* st, int N, int d, bool need_grad) {
+constexpr int MAX_TRAIN_STREAMS = 4;
+
+// shared problem: st->f_prob = [y Np][noise2 Np][X_ N*d][ell of each theta: B x MAX_DIM]
+// per-set vec:    [alpha Np][t Np][T N*d][ell MAX_DIM][scal 8][grad MAX_DIM+8][info 2]
+//                 [Winv nb*128*128][partial nb32*nb32*P]
+static TrainBuffers carve(gpry_state* st, int set, int N, int d, bool need_grad, int B) {
   TrainBuffers b;
   b.N = N;
   b.d = d;
   b.Np = round_up(N, NB);
   b.nb = b.Np / NB;
   const size_t Np = b.Np;
-  st->f_K.reserve(Np * Np);
-  st->f_VT.reserve(Np * Np);
-  if (need_grad) st->f_W.reserve(Np * Np);
+  while ((int)st->f_sets.size() <= set) {
+    TrainSet* ts = new TrainSet();
+    GPRY_CUDA(cudaStreamCreateWithFlags(&ts->stream, cudaStreamNonBlocking));
+    st->f_sets.push_back(ts);
+  }
+  TrainSet* ts = st->f_sets[set];
+  ts->K.reserve(Np * Np);
+  ts->VT.reserve(Np * Np);
+  if (need_grad) ts->W.reserve(Np * Np);
   const int nb32 = (N + 31) / 32;
   const int P = d + 1;
-  size_t n = 4 * Np + 2 * (size_t)N * d + MAX_DIM + 8 + (MAX_DIM + 8) + 2 +
-             (size_t)b.nb * NB * NB + (need_grad ? (size_t)nb32 * nb32 * P : 0) + 64;
-  st->f_vec.reserve(n);
-  double* p = st->f_vec.p;
+  size_t n = 2 * Np + (size_t)N * d + MAX_DIM + 8 + (MAX_DIM + 8) + 2 + (size_t)b.nb * NB * NB +
+             (need_grad ? (size_t)nb32 * nb32 * P : 0) + 64;
+  ts->vec.reserve(n);
+  st->f_prob.reserve(2 * Np + (size_t)N * d + (size_t)B * MAX_DIM);
+  b.y = st->f_prob.p;
+  b.noise2 = b.y + Np;
+  b.X = b.noise2 + Np;
+  double* p = ts->vec.p;
   b.alpha = p; p += Np;
   b.t = p; p += Np;
-  b.y = p; p += Np;
-  b.noise2 = p; p += Np;
-  b.X = p; p += (size_t)N * d;
   b.T = p; p += (size_t)N * d;
   b.ell = p; p += MAX_DIM;
   b.scal = p; p += 8;
@@ -512,19 +639,32 @@ static TrainBuffers carve(gpry_state* st, int N, int d, bool need_grad) {
   b.info = reinterpret_cast<int*>(p); p += 2;
   b.Winv = p; p += (size_t)b.nb * NB * NB;
   b.partial = p;
-  b.K = st->f_K.p;
-  b.VT = st->f_VT.p;
-  b.W = need_grad ? st->f_W.p : nullptr;
+  b.K = ts->K.p;
+  b.VT = ts->VT.p;
+  b.W = need_grad ? ts->W.p : nullptr;
+  b.stream = ts->stream;
   return b;
 }
 
 static void upload_problem(gpry_state* st, TrainBuffers& b, const double* X, const double* noise2,
                            const double* y, cudaStream_t s) {
   const size_t Np = b.Np;
-  GPRY_CUDA(cudaMemsetAsync(b.alpha, 0, 4 * Np * 8, s));
+  GPRY_CUDA(cudaMemsetAsync(b.y, 0, 2 * Np * 8, s));
   GPRY_CUDA(cudaMemcpyAsync(b.X, X, (size_t)b.N * b.d * 8, cudaMemcpyHostToDevice, s));
   GPRY_CUDA(cudaMemcpyAsync(b.noise2, noise2, (size_t)b.N * 8, cudaMemcpyHostToDevice, s));
   GPRY_CUDA(cudaMemcpyAsync(b.y, y, (size_t)b.N * 8, cudaMemcpyHostToDevice, s));
+}
+
+// exp(theta[1:]) of all B evaluations -> device (one pageable copy, before any kernel runs)
+static double* upload_ells(gpry_state* st, const TrainBuffers& b, const double* thetas, int B,
+                           cudaStream_t s) {
+  const int P = b.d + 1;
+  std::vector<double> ells((size_t)B * MAX_DIM, 1.0);
+  for (int i = 0; i < B; i++)
+    for (int k = 0; k < b.d; k++) ells[(size_t)i * MAX_DIM + k] = exp(thetas[(size_t)i * P + 1 + k]);
+  double* dst = b.X + (size_t)b.N * b.d;
+  GPRY_CUDA(cudaMemcpyAsync(dst, ells.data(), ells.size() * 8, cudaMemcpyHostToDevice, s));
+  return dst;
 }
 
 template <int KIND>
@@ -546,13 +686,11 @@ static void launch_grad(const TrainBuffers& b, double c, int nb32, cudaStream_t 
 
 // K(theta) -> L (in K), VT = L^-T, alpha, scal = {sum log diag L, y.alpha}; optionally
 // W = K^-1 and grad (device).  Returns nothing; info stays on the device.
+// b.ell must already point at the device copy of exp(theta[1:]) for this evaluation.
 static void factorize_on_device(gpry_state* st, TrainBuffers& b, int kind, const double* theta,
                                 bool need_grad, cudaStream_t s) {
   const int N = b.N, d = b.d, Np = b.Np, nb = b.nb;
-  std::vector<double> ell(d);
   const double c = exp(theta[0]);
-  for (int k = 0; k < d; k++) ell[k] = exp(theta[1 + k]);
-  GPRY_CUDA(cudaMemcpyAsync(b.ell, ell.data(), d * 8, cudaMemcpyHostToDevice, s));
   GPRY_CUDA(cudaMemsetAsync(b.info, 0, 8, s));
   scale_rows_kernel<<<(N * d + 255) / 256, 256, 0, s>>>(b.X, N, d, b.ell, b.T);
   GPRY_CUDA(cudaGetLastError());
@@ -568,13 +706,13 @@ static void factorize_on_device(gpry_state* st, TrainBuffers& b, int kind, const
   }
   GPRY_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(GemmSmem)));
-  const size_t potf2_smem = 128 * 129 * 8;
+  const size_t potf2_smem = 20 * (size_t)SB_DOUBLES * 8;
   GPRY_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)potf2_smem));
   for (int j = 0; j < nb; j++) {
     double* Ajj = b.K + (size_t)j * NB * (Np + 1);
     double* Wj = b.Winv + (size_t)j * NB * NB;
-    potf2_inv_kernel<<<1, 128, potf2_smem, s>>>(Ajj, Np, Wj, j * NB, b.info);
+    potf2_inv_kernel<<<1, 256, potf2_smem, s>>>(Ajj, Np, Wj, j * NB, b.info);
     GPRY_CUDA(cudaGetLastError());
     const int rem = Np - (j + 1) * NB;
     if (rem > 0) {
@@ -624,7 +762,7 @@ static void factorize_on_device(gpry_state* st, TrainBuffers& b, int kind, const
     }
   }
   // alpha = V^T (V y)
-  gemv_vt_t_kernel<<<(Np + 127) / 128, 128, 0, s>>>(b.VT, Np, N, b.y, b.t);
+  gemv_vt_t_kernel<<<Np / 32, 256, 0, s>>>(b.VT, Np, N, b.y, b.t);
   GPRY_CUDA(cudaGetLastError());
   gemv_vt_kernel<<<(Np * 32 + 255) / 256, 256, 0, s>>>(b.VT, Np, N, b.t, b.alpha);
   GPRY_CUDA(cudaGetLastError());
@@ -655,10 +793,11 @@ void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_tr
   GPRY_CHECK_ARG(kind >= 0 && kind <= 2, "unknown kernel kind");
   GPRY_CHECK_ARG(N >= 1 && d >= 1 && d <= MAX_DIM, "need N >= 1 and 1 <= d <= 128");
   GPRY_CUDA(cudaSetDevice(st->device));
-  cudaStream_t s = 0;
   st->f_valid = false;
-  TrainBuffers b = carve(st, N, d, false);
+  TrainBuffers b = carve(st, 0, N, d, false, 1);
+  cudaStream_t s = b.stream;
   upload_problem(st, b, X_train_t, noise2, y_t, s);
+  b.ell = upload_ells(st, b, theta, 1, s);
   factorize_on_device(st, b, kind, theta, false, s);
   int h_info[2] = {0, 0};
   double scal[2];
@@ -690,42 +829,67 @@ void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_tr
   }
 }
 
+// B hyper-parameter vectors are evaluated round-robin on up to MAX_TRAIN_STREAMS streams with
+// private work sets, so that the latency-bound diagonal-block kernels of one evaluation
+// overlap the GEMMs of the others.  Per-theta results land in pinned host memory.
 void lml_batched_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                         const double* noise2, const double* y_t, const double* thetas, int B,
                         double* out_lml, double* out_grad, int* out_info) {
   GPRY_CHECK_ARG(kind >= 0 && kind <= 2, "unknown kernel kind");
   GPRY_CHECK_ARG(N >= 1 && d >= 1 && d <= MAX_DIM, "need N >= 1 and 1 <= d <= 128");
   GPRY_CUDA(cudaSetDevice(st->device));
-  cudaStream_t s = 0;
   st->f_valid = false;
   const bool need_grad = out_grad != nullptr;
-  TrainBuffers b = carve(st, N, d, need_grad);
-  upload_problem(st, b, X_train_t, noise2, y_t, s);
   const int P = d + 1;
-  std::vector<double> grad(P);
+  const int nset = std::min(B, MAX_TRAIN_STREAMS);
+  std::vector<TrainBuffers> sets;
+  for (int i = 0; i < nset; i++) sets.push_back(carve(st, i, N, d, need_grad, B));
+  // f_prob may have been reallocated by a later carve: refresh the shared pointers
+  for (auto& b : sets) {
+    b.y = st->f_prob.p;
+    b.noise2 = b.y + b.Np;
+    b.X = b.noise2 + b.Np;
+  }
+  const size_t rec = (size_t)P + 4;   // per theta: [info][logdet_half][y.alpha][pad][grad P]
+  if (st->f_pinned_cap < rec * B) {
+    if (st->f_pinned) cudaFreeHost(st->f_pinned);
+    st->f_pinned = nullptr;
+    GPRY_CUDA(cudaMallocHost((void**)&st->f_pinned, rec * B * sizeof(double)));
+    st->f_pinned_cap = rec * B;
+  }
+  if (!st->f_evt) GPRY_CUDA(cudaEventCreateWithFlags(&st->f_evt, cudaEventDisableTiming));
+  upload_problem(st, sets[0], X_train_t, noise2, y_t, sets[0].stream);
+  double* ells = upload_ells(st, sets[0], thetas, B, sets[0].stream);
+  GPRY_CUDA(cudaEventRecord(st->f_evt, sets[0].stream));
+  for (int i = 1; i < nset; i++) GPRY_CUDA(cudaStreamWaitEvent(sets[i].stream, st->f_evt, 0));
   for (int i = 0; i < B; i++) {
+    TrainBuffers& b = sets[i % nset];
+    cudaStream_t s = b.stream;
+    b.ell = ells + (size_t)i * MAX_DIM;
     factorize_on_device(st, b, kind, thetas + (size_t)i * P, need_grad, s);
-    int h_info[2] = {0, 0};
-    double scal[2];
-    GPRY_CUDA(cudaMemcpyAsync(h_info, b.info, 8, cudaMemcpyDeviceToHost, s));
-    GPRY_CUDA(cudaMemcpyAsync(scal, b.scal, 16, cudaMemcpyDeviceToHost, s));
-    if (need_grad)
-      GPRY_CUDA(cudaMemcpyAsync(grad.data(), b.grad, P * 8, cudaMemcpyDeviceToHost, s));
-    GPRY_CUDA(cudaStreamSynchronize(s));
-    out_info[i] = h_info[0];
-    if (h_info[0] != 0) {   // sklearn:_gpr.py:592-593
+    double* r = st->f_pinned + rec * i;
+    GPRY_CUDA(cudaMemcpyAsync(r, b.info, 8, cudaMemcpyDeviceToHost, s));
+    GPRY_CUDA(cudaMemcpyAsync(r + 1, b.scal, 16, cudaMemcpyDeviceToHost, s));
+    if (need_grad) GPRY_CUDA(cudaMemcpyAsync(r + 4, b.grad, P * 8, cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < nset; i++) GPRY_CUDA(cudaStreamSynchronize(sets[i].stream));
+  for (int i = 0; i < B; i++) {
+    const double* r = st->f_pinned + rec * i;
+    const int h_info = *reinterpret_cast<const int*>(r);
+    out_info[i] = h_info;
+    if (h_info != 0) {   // sklearn:_gpr.py:592-593
       out_lml[i] = -INFINITY;
       if (need_grad)
         for (int p = 0; p < P; p++) out_grad[(size_t)i * P + p] = 0.0;
       continue;
     }
     // -0.5 y^T alpha - sum(log diag L) - N/2 log(2 pi)        (sklearn:_gpr.py:613-617)
-    double lml = -0.5 * scal[1];
-    lml -= scal[0];
+    double lml = -0.5 * r[2];
+    lml -= r[1];
     lml -= N / 2.0 * log(2.0 * M_PI);
     out_lml[i] = lml;
     if (need_grad)
-      for (int p = 0; p < P; p++) out_grad[(size_t)i * P + p] = grad[p];
+      for (int p = 0; p < P; p++) out_grad[(size_t)i * P + p] = r[4 + p];
   }
 }
 
