@@ -118,7 +118,8 @@ int gpry_state_destroy(gpry_state* st) {
     st->Vt.release(); st->Ks.release(); st->meanp.release(); st->ssqp.release();
     st->Xdev.release(); st->o_mean.release(); st->o_std.release(); st->o_acq.release();
     for (int b = 0; b < 2; b++) { st->tk_keys[b].release(); st->tk_idx[b].release(); }
-    st->tmp.release(); st->small.release();
+    st->tmp.release(); st->small.release(); st->Vrm.release();
+    st->pc_U.release(); st->pc_Ks.release(); st->pc_UT.release(); st->pc_G.release();
     for (auto* ts : st->f_sets) {
       ts->K.release(); ts->VT.release(); ts->W.release(); ts->vec.release();
       if (ts->stream) cudaStreamDestroy(ts->stream);
@@ -297,6 +298,43 @@ int gpry_mean_grad(gpry_state* st, const double* x, double* out_grad) {
   return guarded([&] {
     GPRY_CHECK_ARG(st && x && out_grad, "NULL argument");
     mean_grad_device(st, x, out_grad);
+  });
+}
+
+int gpry_posterior_cov(gpry_state* st, const double* X, int Ka, int where, double* out_cov,
+                       void* stream) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && X && out_cov, "NULL argument");
+    if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+    cudaStream_t s = (cudaStream_t)stream;
+    GPRY_CUDA(cudaSetDevice(st->device));
+    const bool x_dev = where & GPRY_X_ON_DEVICE, o_dev = where & GPRY_OUT_ON_DEVICE;
+    const double* dX = stage_in(st, X, (size_t)Ka * st->d, x_dev, st->Xdev, s);
+    double* d_out = out_cov;
+    if (!o_dev) {
+      st->o_acq.reserve((size_t)Ka * Ka);
+      d_out = st->o_acq.p;
+    }
+    posterior_cov_device(st, dX, Ka, d_out, s);
+    if (!o_dev)
+      GPRY_CUDA(cudaMemcpyAsync(out_cov, d_out, (size_t)Ka * Ka * 8, cudaMemcpyDeviceToHost, s));
+    if (!o_dev || st->profiling) GPRY_CUDA(cudaStreamSynchronize(s));
+    if (st->profiling) resolve_timings(st);
+  });
+}
+
+int gpry_kernel_cross(gpry_state* st, int kind, int d, const double* theta, const double* X,
+                      int M, const double* Y, int N, double* out) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && theta && X && Y && out, "NULL argument");
+    kernel_cross_device(st, kind, d, theta, X, M, Y, N, out);
+  });
+}
+
+int gpry_kernel_gradient_x(gpry_state* st, const double* x_t, double* out) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && x_t && out, "NULL argument");
+    kernel_gradx_device(st, x_t, out);
   });
 }
 

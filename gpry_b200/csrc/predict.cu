@@ -460,6 +460,18 @@ __global__ void pack_v_kernel(const double* __restrict__ V, int N, int ld, int t
   Vt[e] = v;
 }
 
+// zero-padded row-major copy of the lower triangle of V (or of its transpose)
+__global__ void pad_v_rowmajor_kernel(const double* __restrict__ V, int N, int ld, int transposed,
+                                      int Np, double* __restrict__ out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Np * Np) return;
+  int row = (int)(e / Np), col = (int)(e % Np);
+  double v = 0.0;
+  if (row < N && col <= row)
+    v = transposed ? V[(size_t)col * ld + row] : V[(size_t)row * ld + col];
+  out[e] = v;
+}
+
 __global__ void pad_copy_kernel(const double* __restrict__ src, int n, int npad,
                                 double* __restrict__ dst) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -540,6 +552,13 @@ void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_
   pack_v_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Vsrc, N, ldV, transposed, st->nJ,
                                                                st->Vt.p);
   GPRY_CUDA(cudaGetLastError());
+  {
+    int64_t tot = (int64_t)st->Npad * st->Npad;
+    st->Vrm.reserve((size_t)tot);
+    pad_v_rowmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(Vsrc, N, ldV, transposed,
+                                                                       st->Npad, st->Vrm.p);
+    GPRY_CUDA(cudaGetLastError());
+  }
   GPRY_CUDA(cudaStreamSynchronize(s));
   st->loaded = true;
 }
@@ -714,6 +733,210 @@ void mean_grad_device(gpry_state* st, const double* x_host, double* out_host) {
   }
   GPRY_CUDA(cudaGetLastError());
   GPRY_CUDA(cudaMemcpyAsync(out_host, out, d * 8, cudaMemcpyDeviceToHost, s));
+  GPRY_CUDA(cudaStreamSynchronize(s));
+}
+
+// ---------------------------------------------------------------------------------------
+// Posterior covariance among a small set of candidates (Kriging-believer conditioning of the
+// ranked pool, gp_acquisition.py:1464-1494, 1522-1555, 1598-1670): instead of re-factorising
+// the model augmented with the pool points, the conditioned variance follows from
+//   Sigma = k(Xa, Xa) - (V K*a^T)^T (V K*a^T)        (normalised units, no noise term)
+// as  var(a | P) = Sigma_aa - Sigma_aP (Sigma_PP + noise I)^-1 Sigma_Pa  (host, |P| <= size).
+// ---------------------------------------------------------------------------------------
+// scaled coordinates U[a][k] = ((x - min) / width) / ell, zero padded to [rows_pad][DP]
+__global__ void scale_candidates_kernel(const double* __restrict__ X, int Ka, int d, int rows_pad,
+                                        int DP, const double* __restrict__ prm,
+                                        double* __restrict__ U) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows_pad * DP) return;
+  int a = e / DP, k = e % DP;
+  double v = 0.0;
+  if (a < Ka && k < d) {
+    double x = X[(size_t)a * d + k];
+    v = ((x - prm[k]) / prm[MAX_DIM + k]) / prm[2 * MAX_DIM + k];
+  }
+  U[e] = v;
+}
+
+// out[a][j] = c g(|A_a - B_j|) for a < nA, j < nB, else 0; out is [rows_pad][ld] row major.
+// If sub != nullptr: out = value - sub[a][j] (same layout).  grid (ld/128, rows_pad/8).
+template <int KIND>
+__global__ void __launch_bounds__(128)
+kcross_kernel(const double* __restrict__ A, int nA, const double* __restrict__ B, int nB, int DP,
+              double c, int ld, const double* __restrict__ sub, double* __restrict__ out) {
+  extern __shared__ double sh[];
+  double* Bs = sh;                     // [128][DP+1]
+  double* As = sh + 128 * (DP + 1);    // [8][DP]
+  const int tid = threadIdx.x;
+  const int j0 = blockIdx.x * 128, a0 = blockIdx.y * 8;
+  for (int e = tid; e < 128 * DP; e += 128) {
+    int r = e / DP, k = e % DP;
+    Bs[r * (DP + 1) + k] = B[(size_t)(j0 + r) * DP + k];
+  }
+  for (int e = tid; e < 8 * DP; e += 128) As[e] = A[(size_t)a0 * DP + e];
+  __syncthreads();
+  const int j = j0 + tid;
+  for (int q = 0; q < 8; q++) {
+    const int a = a0 + q;
+    double v = 0.0;
+    if (a < nA && j < nB) {
+      double r2 = 0.0;
+      for (int k = 0; k < DP; k++) {
+        double df = As[q * DP + k] - Bs[tid * (DP + 1) + k];
+        r2 = fma(df, df, r2);
+      }
+      v = kernel_value<KIND>(r2, c);
+      if (sub) v -= sub[(size_t)a * ld + j];
+    }
+    out[(size_t)a * ld + j] = v;
+  }
+}
+
+static void launch_kcross(int kind, const double* A, int nA, int rowsA_pad, const double* B, int nB,
+                          int DP, double c, int ld, const double* sub, double* out,
+                          cudaStream_t s) {
+  dim3 grid(ld / 128, rowsA_pad / 8);
+  size_t smem = ((size_t)128 * (DP + 1) + 8 * DP) * 8;
+  switch (kind) {
+    case GPRY_KERNEL_RBF:
+      if (smem > 48 * 1024)
+        GPRY_CUDA(cudaFuncSetAttribute(kcross_kernel<GPRY_KERNEL_RBF>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kcross_kernel<GPRY_KERNEL_RBF><<<grid, 128, smem, s>>>(A, nA, B, nB, DP, c, ld, sub, out);
+      break;
+    case GPRY_KERNEL_MATERN15:
+      if (smem > 48 * 1024)
+        GPRY_CUDA(cudaFuncSetAttribute(kcross_kernel<GPRY_KERNEL_MATERN15>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kcross_kernel<GPRY_KERNEL_MATERN15><<<grid, 128, smem, s>>>(A, nA, B, nB, DP, c, ld, sub,
+                                                                 out);
+      break;
+    default:
+      if (smem > 48 * 1024)
+        GPRY_CUDA(cudaFuncSetAttribute(kcross_kernel<GPRY_KERNEL_MATERN25>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kcross_kernel<GPRY_KERNEL_MATERN25><<<grid, 128, smem, s>>>(A, nA, B, nB, DP, c, ld, sub,
+                                                                 out);
+  }
+  GPRY_CUDA(cudaGetLastError());
+}
+
+// d_out: [Ka][Ka] row major (device)
+void posterior_cov_device(gpry_state* st, const double* dX, int Ka, double* d_out,
+                          cudaStream_t s) {
+  if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+  GPRY_CHECK_ARG(Ka >= 1 && Ka <= 8192, "posterior covariance: 1 <= Ka <= 8192");
+  GPRY_CUDA(cudaSetDevice(st->device));
+  const int Kap = round_up(Ka, TILE_ROWS), Np = st->Npad, DP = st->DP, d = st->d;
+  st->pc_U.reserve((size_t)Kap * DP);
+  st->pc_Ks.reserve((size_t)Kap * std::max(Np, Kap));
+  st->pc_UT.reserve((size_t)Kap * Np);
+  st->pc_G.reserve((size_t)Kap * Kap);
+  TimedScope ts(st, s, T_FINISH, 5);
+  scale_candidates_kernel<<<(Kap * DP + 255) / 256, 256, 0, s>>>(dX, Ka, d, Kap, DP, st->prm_dev.p,
+                                                                 st->pc_U.p);
+  GPRY_CUDA(cudaGetLastError());
+  // K*a (row major, zero padded)
+  launch_kcross(st->kind, st->pc_U.p, Ka, Kap, st->T.p, st->N, DP, st->c, Np, nullptr, st->pc_Ks.p,
+                s);
+  // UT = K*a V^T   (UT[a][j] = sum_k K*[a][k] V[j][k])
+  gemm_nt(st->pc_Ks.p, Np, st->Vrm.p, Np, st->pc_UT.p, Np, Kap, Np, Np, 1.0, 0, 0, 0, s);
+  // G = UT UT^T
+  gemm_nt(st->pc_UT.p, Np, st->pc_UT.p, Np, st->pc_G.p, Kap, Kap, Kap, Np, 1.0, 0, 0, 0, s);
+  // Sigma = k(Xa, Xa) - G  -> pc_Ks reused as [Kap][Kap]
+  launch_kcross(st->kind, st->pc_U.p, Ka, Kap, st->pc_U.p, Ka, DP, st->c, Kap, st->pc_G.p,
+                st->pc_Ks.p, s);
+  GPRY_CUDA(cudaMemcpy2DAsync(d_out, (size_t)Ka * 8, st->pc_Ks.p, (size_t)Kap * 8, (size_t)Ka * 8,
+                              Ka, cudaMemcpyDeviceToDevice, s));
+}
+
+// k_theta(X, Y) for arbitrary host inputs (already transformed): Product.__call__
+// sklearn:kernels.py:971.  Host in, host out; API completeness, not a hot path.
+void kernel_cross_device(gpry_state* st, int kind, int d, const double* theta, const double* hX,
+                         int M, const double* hY, int N, double* h_out) {
+  GPRY_CHECK_ARG(kind >= 0 && kind <= 2 && d >= 1 && d <= MAX_DIM && M >= 1 && N >= 1,
+                 "bad kernel_cross arguments");
+  GPRY_CUDA(cudaSetDevice(st->device));
+  cudaStream_t s = 0;
+  const int DP = round_up(d, 4), Mp = round_up(M, 8), Npd = round_up(N, 128);
+  std::vector<double> A((size_t)Mp * DP, 0.0), B((size_t)Npd * DP, 0.0);
+  const double c = exp(theta[0]);
+  for (int i = 0; i < M; i++)
+    for (int k = 0; k < d; k++) A[(size_t)i * DP + k] = hX[(size_t)i * d + k] / exp(theta[1 + k]);
+  for (int j = 0; j < N; j++)
+    for (int k = 0; k < d; k++) B[(size_t)j * DP + k] = hY[(size_t)j * d + k] / exp(theta[1 + k]);
+  st->pc_U.reserve(A.size());
+  st->pc_UT.reserve(B.size());
+  st->pc_Ks.reserve((size_t)Mp * Npd);
+  GPRY_CUDA(cudaMemcpyAsync(st->pc_U.p, A.data(), A.size() * 8, cudaMemcpyHostToDevice, s));
+  GPRY_CUDA(cudaMemcpyAsync(st->pc_UT.p, B.data(), B.size() * 8, cudaMemcpyHostToDevice, s));
+  launch_kcross(kind, st->pc_U.p, M, Mp, st->pc_UT.p, N, DP, c, Npd, nullptr, st->pc_Ks.p, s);
+  GPRY_CUDA(cudaMemcpy2DAsync(h_out, (size_t)N * 8, st->pc_Ks.p, (size_t)Npd * 8, (size_t)N * 8, M,
+                              cudaMemcpyDeviceToHost, s));
+  GPRY_CUDA(cudaStreamSynchronize(s));
+}
+
+// d k(x, X_train) / d x_ for one point: (N x d) row major (Kernel.gradient_x, kernels.py:
+// 257-278, 363-432, 687-699).  Thread per (j, k).
+template <int KIND>
+__global__ void gradx_kernel(const double* __restrict__ Xt, int N, int d,
+                             const double* __restrict__ x_t, const double* __restrict__ ell,
+                             double c, double* __restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * d) return;
+  const int j = e / d, k = e % d;
+  double r2 = 0.0, dk = 0.0;
+  for (int q = 0; q < d; q++) {
+    double diff = (x_t[q] - Xt[(size_t)j * d + q]) / ell[q];
+    r2 = fma(diff, diff, r2);
+    if (q == k) dk = diff;
+  }
+  double g;
+  if (KIND == GPRY_KERNEL_RBF) {
+    g = (-exp(-0.5 * r2) * dk) / ell[k];
+  } else if (KIND == GPRY_KERNEL_MATERN15) {
+    double dist = sqrt(r2);
+    double s3d = 1.7320508075688772 * dist;
+    double by = dist != 0.0 ? 1.7320508075688772 / dist : 0.0;
+    g = exp(-s3d) * ((dk / ell[k]) * by) * (1.0 - (1.0 + s3d));
+  } else {
+    double dist = sqrt(r2);
+    double s5d = 2.23606797749979 * dist;
+    double f = (5.0 / 3.0) * r2 + s5d + 1.0;
+    double inv = dist != 0.0 ? 2.23606797749979 * (1.0 / dist) : 0.0;
+    double dl = dk / ell[k];
+    double f1g = inv * dl, f2g = (10.0 / 3.0) * dl;
+    double gg = exp(-s5d);
+    g = f * (-gg * f1g) + gg * (f1g + f2g);
+  }
+  out[e] = c * g;
+}
+
+void kernel_gradx_device(gpry_state* st, const double* x_host, double* out_host) {
+  if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+  GPRY_CUDA(cudaSetDevice(st->device));
+  const int d = st->d, N = st->N;
+  cudaStream_t s = 0;
+  st->small.reserve(2 * MAX_DIM);
+  st->tmp.reserve((size_t)N * d);
+  GPRY_CUDA(cudaMemcpyAsync(st->small.p, x_host, d * 8, cudaMemcpyHostToDevice, s));
+  const double* ell = st->prm_dev.p + 2 * MAX_DIM;
+  const int nblk = (N * d + 255) / 256;
+  switch (st->kind) {
+    case GPRY_KERNEL_RBF:
+      gradx_kernel<GPRY_KERNEL_RBF><<<nblk, 256, 0, s>>>(st->Xt.p, N, d, st->small.p, ell, st->c,
+                                                        st->tmp.p);
+      break;
+    case GPRY_KERNEL_MATERN15:
+      gradx_kernel<GPRY_KERNEL_MATERN15><<<nblk, 256, 0, s>>>(st->Xt.p, N, d, st->small.p, ell,
+                                                             st->c, st->tmp.p);
+      break;
+    default:
+      gradx_kernel<GPRY_KERNEL_MATERN25><<<nblk, 256, 0, s>>>(st->Xt.p, N, d, st->small.p, ell,
+                                                             st->c, st->tmp.p);
+  }
+  GPRY_CUDA(cudaGetLastError());
+  GPRY_CUDA(cudaMemcpyAsync(out_host, st->tmp.p, (size_t)N * d * 8, cudaMemcpyDeviceToHost, s));
   GPRY_CUDA(cudaStreamSynchronize(s));
 }
 

@@ -81,6 +81,8 @@ struct gpry_state {
   gpry::DevBuf<double> Xt;               // [N][d]      X_train_ (un-scaled, gradient kernel)
   gpry::DevBuf<double> alpha;            // [Npad]
   gpry::DevBuf<double> Vt;               // tiled lower block triangle of V = L^-1
+  gpry::DevBuf<double> Vrm;              // [Npad][Npad] row-major V, zero padded (posterior cov)
+  gpry::DevBuf<double> pc_U, pc_Ks, pc_UT, pc_G;   // posterior-covariance scratch
 
   // scratch (grown on demand, reused across calls)
   gpry::DevBuf<double> Ks;               // [chunk_tiles][nKT] K* tiles
@@ -133,6 +135,10 @@ void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_
                   const double* VT_dev_rowmajor, int ldV, const double* alpha_dev, double c,
                   const double* ell, const double* x_min, const double* x_width, double y_mean,
                   double y_std, double clip_hi);
+void posterior_cov_device(gpry_state* st, const double* dX, int Ka, double* d_out, cudaStream_t s);
+void kernel_cross_device(gpry_state* st, int kind, int d, const double* theta, const double* hX,
+                         int M, const double* hY, int N, double* h_out);
+void kernel_gradx_device(gpry_state* st, const double* x_host, double* out_host);
 // topk.cu
 int64_t topk_device(gpry_state* st, const double* d_scores, int64_t M, int Kp, int64_t idx_base,
                     double** d_keys_out, int64_t** d_idx_out, cudaStream_t s);
@@ -140,6 +146,8 @@ void gather_topk(gpry_state* st, const int64_t* d_idx, int64_t n, int64_t idx_ba
                  const double* dX, int d, const double* d_mean, const double* d_std,
                  double* o_mean, double* o_std, double* o_X, cudaStream_t s);
 // train.cu
+void gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N,
+             int K, double alpha, int accumulate, int lower_only, int klo_row, cudaStream_t s);
 void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                       const double* noise2, const double* y_t, const double* theta,
                       double* out_L, double* out_V, double* out_alpha, double* out_logdet_half,

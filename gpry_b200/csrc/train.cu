@@ -378,6 +378,18 @@ static void launch_gemm(const GemmArgs& g, cudaStream_t s) {
   GPRY_CUDA(cudaGetLastError());
 }
 
+void gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N,
+             int K, double alpha, int accumulate, int lower_only, int klo_row, cudaStream_t s) {
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.accumulate = accumulate;
+  g.filter = lower_only ? G_FILTER_LOWER : G_FILTER_ALL;
+  g.klo_mode = klo_row ? G_KLO_ROW : G_KLO_ZERO;
+  GPRY_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(GemmSmem)));
+  launch_gemm(g, s);
+}
+
 // ---------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------
@@ -622,21 +634,23 @@ static TrainBuffers carve(gpry_state* st, int set, int N, int d, bool need_grad,
   if (need_grad) ts->W.reserve(Np * Np);
   const int nb32 = (N + 31) / 32;
   const int P = d + 1;
-  size_t n = 2 * Np + (size_t)N * d + MAX_DIM + 8 + (MAX_DIM + 8) + 2 + (size_t)b.nb * NB * NB +
+  auto al = [](size_t x) { return (x + 31) / 32 * 32; };   // 256-byte aligned segments
+  const size_t nXd = al((size_t)N * d);
+  size_t n = 2 * Np + nXd + al(MAX_DIM) + 32 + al(MAX_DIM + 8) + 32 + (size_t)b.nb * NB * NB +
              (need_grad ? (size_t)nb32 * nb32 * P : 0) + 64;
   ts->vec.reserve(n);
-  st->f_prob.reserve(2 * Np + (size_t)N * d + (size_t)B * MAX_DIM);
+  st->f_prob.reserve(2 * Np + nXd + (size_t)B * MAX_DIM);
   b.y = st->f_prob.p;
   b.noise2 = b.y + Np;
   b.X = b.noise2 + Np;
   double* p = ts->vec.p;
   b.alpha = p; p += Np;
   b.t = p; p += Np;
-  b.T = p; p += (size_t)N * d;
-  b.ell = p; p += MAX_DIM;
-  b.scal = p; p += 8;
-  b.grad = p; p += MAX_DIM + 8;
-  b.info = reinterpret_cast<int*>(p); p += 2;
+  b.T = p; p += nXd;
+  b.ell = p; p += al(MAX_DIM);
+  b.scal = p; p += 32;
+  b.grad = p; p += al(MAX_DIM + 8);
+  b.info = reinterpret_cast<int*>(p); p += 32;
   b.Winv = p; p += (size_t)b.nb * NB * NB;
   b.partial = p;
   b.K = ts->K.p;
@@ -662,7 +676,7 @@ static double* upload_ells(gpry_state* st, const TrainBuffers& b, const double* 
   std::vector<double> ells((size_t)B * MAX_DIM, 1.0);
   for (int i = 0; i < B; i++)
     for (int k = 0; k < b.d; k++) ells[(size_t)i * MAX_DIM + k] = exp(thetas[(size_t)i * P + 1 + k]);
-  double* dst = b.X + (size_t)b.N * b.d;
+  double* dst = b.X + ((size_t)b.N * b.d + 31) / 32 * 32;
   GPRY_CUDA(cudaMemcpyAsync(dst, ells.data(), ells.size() * 8, cudaMemcpyHostToDevice, s));
   return dst;
 }

@@ -26,6 +26,17 @@ def _stream_ptr(stream):
     return C.c_void_p(stream.cuda_stream)  # torch.cuda.Stream
 
 
+_workspaces = {}
+
+
+def workspace(device=0):
+    """Process-wide DeviceGP whose big training-side buffers are shared by every regressor
+    instance of this process (factorizations, LML, stand-alone kernel evaluations)."""
+    if device not in _workspaces:
+        _workspaces[device] = DeviceGP(device)
+    return _workspaces[device]
+
+
 class DeviceGP:
     """Opaque device state + the hot-path calls.  Not picklable by design: the owning
     ``GaussianProcessRegressor`` keeps it outside of its pickled/deep-copied attributes and
@@ -175,6 +186,35 @@ class DeviceGP:
             raise ValueError(f"x must have {self.d} entries")
         out = np.empty(self.d)
         check(self._lib.gpry_mean_grad(self._h, ptr(x), ptr(out)))
+        return out
+
+    def posterior_cov(self, X, stream=None):
+        """Posterior covariance (normalised units, no noise) among the rows of X (Ka <= 8192)."""
+        X, Ka, where = self._prep_X(X)
+        if where & _lib.X_ON_DEVICE:
+            import torch
+            out = torch.empty((Ka, Ka), dtype=torch.float64, device=X.device)
+            where |= _lib.OUT_ON_DEVICE
+        else:
+            out = np.empty((Ka, Ka))
+        check(self._lib.gpry_posterior_cov(self._h, ptr(X), Ka, where, ptr(out),
+                                           _stream_ptr(stream)))
+        return out
+
+    def kernel_cross(self, kind, theta, X_, Y_):
+        """k_theta(X_, Y_) for transformed host arrays (no uploaded model needed)."""
+        X_, Y_ = as_f64(np.atleast_2d(X_)), as_f64(np.atleast_2d(Y_))
+        theta = as_f64(theta, (X_.shape[1] + 1,))
+        out = np.empty((X_.shape[0], Y_.shape[0]))
+        check(self._lib.gpry_kernel_cross(self._h, KERNEL_KINDS[kind], X_.shape[1], ptr(theta),
+                                          ptr(X_), X_.shape[0], ptr(Y_), Y_.shape[0], ptr(out)))
+        return out
+
+    def kernel_gradient_x(self, x_t):
+        """d k(x_, X_train_)/d x_ (N x d) of the uploaded model at a transformed point."""
+        x_t = as_f64(x_t).reshape(-1)
+        out = np.empty((self.N, self.d))
+        check(self._lib.gpry_kernel_gradient_x(self._h, ptr(x_t), ptr(out)))
         return out
 
     # ------------------------------------------------------------------ training side

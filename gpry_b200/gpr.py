@@ -1,0 +1,748 @@
+"""
+``GaussianProcessRegressor`` with the interface of ``gpry.gpr.GaussianProcessRegressor``
+(reference gpr.py:27-1488) whose arithmetic runs on a B200 through ``libgpry_b200.so``.
+
+What stays on the host (exactly as in the reference, O(N) or control flow): data
+bookkeeping in ``append_to_data`` (:577-753), pre-processor scalars, the infinities
+classifier and trust-region masks around ``predict`` (:1104-1174, 1196-1201), evaluation
+counters (:1088, 880, 1296), the L-BFGS-B driver of ``fit_gpr_hyperparameters`` (:883-994).
+
+What runs on the GPU: ``predict`` / ``predict_std`` arithmetic (:1176-1227, 1325-1347),
+``_update_model`` + ``_kernel_inverse`` (:996-1020, 1453-1465), ``log_marginal_likelihood``
+and its gradient (:876-881 -> sklearn _gpr.py:541-656), the single-point mean gradient
+(:1236-1242).  There is no CPU fallback for any of these.
+
+The instance stays picklable / deep-copyable like the reference's (:1354-1433, io.py): all
+fitted attributes (``X_train_, y_train_, alpha, alpha_, L_, V_, kernel_`` ...) are numpy
+arrays; the device handle lives outside the copied state and is rebuilt lazily.
+"""
+import os
+import threading
+import warnings
+from copy import deepcopy
+from numbers import Number
+from operator import itemgetter
+
+import numpy as np
+import scipy.optimize
+
+from .device import DeviceGP, workspace
+from .kernels import ConstantKernel as C, RBF, Matern, Product
+from .preprocessing import DummyPreprocessor
+
+
+def default_device():
+    """One process per GPU: LOCAL_RANK (torchrun) or the current torch device, else 0."""
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
+    try:
+        import torch
+        if torch.cuda.is_available() and torch.cuda.is_initialized():
+            return torch.cuda.current_device()
+    except ImportError:
+        pass
+    return 0
+
+
+def is_in_bounds(points, bounds):
+    """tools.py:263-287."""
+    points = np.atleast_2d(points)
+    return np.all((points >= bounds[:, 0]) & (points <= bounds[:, 1]), axis=1)
+
+
+def shrink_bounds(bounds, samples, factor=1):
+    """tools.py:308-361."""
+    bounds = np.atleast_2d(bounds)
+    samples = np.atleast_2d(samples)
+    out = np.empty(shape=bounds.shape, dtype=float)
+    out[:, 0] = samples.min(axis=0)
+    out[:, 1] = samples.max(axis=0)
+    width = out[:, 1] - out[:, 0]
+    delta = (factor - 1) / 2 * width
+    out[:, 0] -= delta
+    out[:, 1] += delta
+    out[:, 0] = np.array([out[:, 0], bounds[:, 0]]).max(axis=0)
+    out[:, 1] = np.array([out[:, 1], bounds[:, 1]]).min(axis=0)
+    return out
+
+
+def check_random_state(seed):
+    """tools.py:134-145 (Generators pass through, else sklearn's ``check_random_state``:
+    None -> numpy's global RandomState, int -> RandomState(seed), RandomState -> itself)."""
+    if isinstance(seed, (np.random.Generator, np.random.RandomState)):
+        return seed
+    if seed is None or seed is np.random:
+        return np.random.mtrand._rand
+    if isinstance(seed, (int, np.integer)):
+        return np.random.RandomState(seed)
+    raise ValueError(f"{seed!r} cannot be used to seed a numpy.random.RandomState instance")
+
+
+def delta_logp_of_1d_nstd(n1, d):
+    """tools.py:100-118."""
+    from scipy.stats import chi2
+    from scipy.special import erfc
+    return 0.5 * chi2.isf(erfc(n1 / np.sqrt(2)), d)
+
+
+class GaussianProcessRegressor:
+    """See the module docstring; constructor arguments as gpr.py:265-271 plus ``device``."""
+
+    def __init__(self, kernel="RBF", output_scale_prior=[1e-2, 1e3],
+                 length_scale_prior=[1e-3, 1e1], noise_level=1e-2, clip_factor=1.1,
+                 optimizer="fmin_l_bfgs_b", n_restarts_optimizer=0,
+                 preprocessing_X=None, preprocessing_y=None,
+                 account_for_inf=None, inf_threshold="20s", keep_min_finite=None,
+                 trust_region_factor=None, trust_region_nstd=None,
+                 bounds=None, random_state=None, verbose=1, device=None):
+        self.n_last_appended = 0
+        self.n_last_appended_finite = 0
+        self.newly_appended_for_inv = 0
+        self.preprocessing_X = DummyPreprocessor if preprocessing_X is None else preprocessing_X
+        self.preprocessing_y = DummyPreprocessor if preprocessing_y is None else preprocessing_y
+        self.noise_level = noise_level
+        if clip_factor is not None and clip_factor < 1:
+            raise ValueError("'clip_factor' must be >= 1, or None for no clippling.")
+        self.clip_factor = clip_factor
+        self.n_eval = 0
+        self.n_eval_loglike = 0
+        self.verbose = verbose
+        self.inf_value = np.inf
+        self.minus_inf_value = -np.inf
+        self._fitted = False
+        if bounds is None:
+            raise ValueError("'bounds' (prior bounds, shape (d, 2)) are required")
+        self.bounds = np.asarray(bounds, dtype=float)
+        self.trust_bounds = None
+        self.trust_region_factor = trust_region_factor
+        self.trust_region_nstd = trust_region_nstd
+        self.optimizer = optimizer
+        self.n_restarts_optimizer = n_restarts_optimizer
+        self.random_state = random_state
+        self.inf_threshold = inf_threshold
+        # Infinities classifier: host-side and out of scope of the B200 path; any object with
+        # the interface of gpry.svm.SVM (fit / predict / _is_finite_raw) can be plugged in.
+        if isinstance(account_for_inf, str) and account_for_inf.lower() == "svm":
+            try:
+                from gpry.svm import SVM   # the reference's own classifier, if installed
+            except ImportError as excpt:
+                raise NotImplementedError(
+                    "account_for_inf='SVM' needs gpry.svm.SVM (host-side classifier, not "
+                    "part of gpry_b200); pass a classifier object or None.") from excpt
+            self.infinities_classifier = SVM(random_state=random_state)
+        elif account_for_inf is False or account_for_inf is None:
+            self.infinities_classifier = None
+        else:
+            self.infinities_classifier = account_for_inf
+        # Auto-construct inbuilt kernels (gpr.py:329-363)
+        if isinstance(kernel, str):
+            kernel = {kernel: {}}
+        if isinstance(kernel, dict):
+            if len(kernel) != 1:
+                raise ValueError("'kernel' must be a single-key dict.")
+            kernel_name = list(kernel)[0]
+            kernel_args = kernel[kernel_name] or {}
+            self.bounds_ = self.preprocessing_X.transform_bounds(self.bounds)
+            try:
+                length_corr_kernel = {"rbf": RBF, "matern": Matern}[kernel_name.lower()]
+            except KeyError as excpt:
+                raise ValueError("Currently only 'RBF' and 'Matern' are supported as "
+                                 f"standard kernels. Got '{kernel_name}'.") from excpt
+            output_scale_init = np.sqrt(output_scale_prior[0] * output_scale_prior[1])
+            length_scale_init = np.sqrt(length_scale_prior[0] * length_scale_prior[1])
+            kernel = (
+                C(output_scale_init ** 2,
+                  [output_scale_prior[0] ** 2, output_scale_prior[1] ** 2])
+                * length_corr_kernel([length_scale_init] * self.d, length_scale_prior,
+                                     prior_bounds=self.bounds_, **kernel_args))
+        if not isinstance(kernel, Product):
+            raise NotImplementedError("kernel must be 'RBF', 'Matern', {'Matern': {'nu': ..}} "
+                                      "or ConstantKernel * RBF/Matern")
+        self.kernel = kernel
+        self.alpha = noise_level ** 2.
+        d = self.d
+        self.X_train, self.y_train = np.empty((0, d)), np.empty((0,))
+        self.X_train_, self.y_train_ = None, None
+        self.X_train_all, self.y_train_all = np.empty((0, d)), np.empty((0,))
+        self.X_train_all_, self.y_train_all_ = None, None
+        self.noise_level_ = None
+        self.kernel_ = None
+        self.keep_min_finite = keep_min_finite if keep_min_finite is not None else max(2, d)
+        self._diff_threshold = None
+        if self.infinities_classifier is not None:
+            if isinstance(inf_threshold, str) and inf_threshold.endswith("s"):
+                self._diff_threshold = delta_logp_of_1d_nstd(float(inf_threshold[:-1]), d)
+            else:
+                self._diff_threshold = float(inf_threshold)
+        self.device = default_device() if device is None else int(device)
+        self._dev = None          # DeviceGP holding the predict state (never pickled)
+        self._dev_dirty = True
+
+    # ------------------------------------------------------------------ pickling / copies
+    _NOT_COPIED = ("_dev", "_dev_dirty")
+
+    def __getstate__(self):
+        state = {k: v for k, v in self.__dict__.items() if k not in self._NOT_COPIED}
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._dev = None
+        self._dev_dirty = True
+
+    def __deepcopy__(self, memo):
+        """Same observable result as gpr.py:1354-1433 (a fresh instance carrying copies of
+        the data and fitted attributes); the device state is rebuilt lazily by the copy."""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in self._NOT_COPIED:
+                continue
+            new.__dict__[k] = deepcopy(v, memo)
+        new._dev = None
+        new._dev_dirty = True
+        return new
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def d(self):
+        if self.bounds is None:
+            return self.X_train.shape[1]
+        return self.bounds.shape[0]
+
+    @property
+    def y_max(self):
+        return np.max(getattr(self, "y_train", [self.minus_inf_value]))
+
+    @property
+    def n(self):
+        return len(getattr(self, "y_train", []))
+
+    n_finite = n
+
+    @property
+    def n_total(self):
+        if self.infinities_classifier:
+            return self.infinities_classifier.n or self.n
+        return self.n
+
+    @property
+    def fitted(self):
+        return self._fitted
+
+    @property
+    def last_appended_finite(self):
+        return (np.copy(self.X_train[-self.n_last_appended_finite:]),
+                np.copy(self.y_train[-self.n_last_appended_finite:]))
+
+    @property
+    def last_appended(self):
+        if self.infinities_classifier is None:
+            return self.last_appended_finite
+        return (np.copy(self.X_train_all[-self.n_last_appended:]),
+                np.copy(self.y_train_all[-self.n_last_appended:]))
+
+    @property
+    def scales(self):
+        return (self.preprocessing_y.inverse_transform_scale(
+            np.sqrt(self.kernel_.k1.constant_value)),
+            tuple(self.preprocessing_X.inverse_transform_scale(self.kernel_.k2.length_scale)))
+
+    def is_finite(self, y):
+        if self.infinities_classifier is None:
+            return np.full(shape=len(y), fill_value=True)
+        return self.infinities_classifier.is_finite(self.preprocessing_y.transform(y))
+
+    def update_trust_region(self):
+        """gpr.py:554-575."""
+        if self.trust_region_factor is None:
+            return
+        if self.trust_region_nstd is None:
+            use_X = self.X_train
+        else:
+            nstd = self.trust_region_nstd
+            use_X = np.empty(shape=(0, self.X_train.shape[1]))
+            while len(use_X) < min(self.d, self.n):
+                use_X = self.X_train[np.where(
+                    max(self.y_train) - self.y_train < delta_logp_of_1d_nstd(nstd, self.d))]
+                nstd = nstd + 0.1
+        self.trust_bounds = shrink_bounds(self.bounds, use_X, factor=self.trust_region_factor)
+
+    # ------------------------------------------------------------------ data
+    def _validate_noise_level(self, noise_level, n_train):
+        """gpr.py:755-785."""
+        if n_train == 0 and noise_level is not None:
+            raise ValueError("noise_level must be None if not fitting to new points.")
+        if np.iterable(noise_level):
+            noise_level = np.atleast_1d(noise_level)
+            if noise_level.shape[0] != n_train:
+                raise ValueError("noise_level must be an array with same number of entries "
+                                 f"as y, but len(n)={noise_level.shape[0]} != len(y)={n_train})")
+        elif isinstance(noise_level, Number):
+            if np.iterable(self.noise_level):
+                noise_level = np.full(fill_value=noise_level, shape=(n_train,))
+        elif noise_level is None:
+            if np.iterable(self.noise_level):
+                raise ValueError("Need to pass non-null noise_level (scalar or array) because "
+                                 "concrete values were given earlier for the training points.")
+        else:
+            raise ValueError("noise_level needs to be an iterable, number or None. "
+                             f"Got type(noise_level)={type(noise_level)}")
+        return noise_level
+
+    def _update_noise_level(self, noise_level):
+        """gpr.py:787-817."""
+        if np.iterable(noise_level):
+            if not np.iterable(self.noise_level):
+                self.noise_level = np.full(fill_value=self.noise_level,
+                                           shape=(len(self.y_train_all) - len(noise_level),))
+            self.noise_level = np.append(self.noise_level, noise_level, axis=0)
+        elif isinstance(noise_level, Number):
+            if not np.isclose(noise_level, self.noise_level):
+                self.noise_level = noise_level
+
+    @staticmethod
+    def _diff_threshold_if_keep_n_finite(y, n, reference_diff_threshold, epsilon=1e-6):
+        """gpr.py:1475-1488."""
+        if n is None or n <= 1:
+            return reference_diff_threshold
+        y_sorted = np.sort(y)
+        difference_to_nth_point = y_sorted[-1] - y_sorted[-min(n, len(y_sorted))]
+        return max(reference_diff_threshold, difference_to_nth_point + epsilon)
+
+    def append_to_data(self, X, y, noise_level=None, fit_gpr=True, fit_classifier=True):
+        """gpr.py:577-753 (same control flow; the two numeric calls at the end run on the
+        GPU)."""
+        fit_preprocessors = False
+        fit_gpr_kwargs = None
+        if fit_gpr is True:
+            fit_classifier = True
+            fit_gpr_kwargs = {}
+        elif str(fit_gpr) == "simple":
+            fit_classifier = True
+            fit_gpr_kwargs = {"simple": True}
+            fit_gpr = True
+        elif isinstance(fit_gpr, dict):
+            fit_classifier = True
+            fit_gpr_kwargs = deepcopy(fit_gpr)
+            fit_gpr = True
+        elif fit_gpr is not False:
+            raise ValueError("`fit_gpr` needs to be bool, 'simple', or a dict of args for the "
+                             f"`fit_gpr_hyperparameters` method. Got {fit_gpr}.")
+        if fit_classifier:
+            fit_preprocessors = True
+        force_fit_gpr = False
+        if X is None and y is None:
+            X, y = np.empty((0, self.d)), np.empty((0,))
+            force_fit_gpr = fit_gpr
+            if noise_level is not None:
+                raise ValueError("Cannot give a noise level if X and y are not given.")
+        elif X is None or y is None:
+            raise ValueError("If passing X, y needs to be passed too, and viceversa.")
+        X = np.atleast_2d(np.asarray(X, dtype=float))
+        y = np.atleast_1d(np.asarray(y, dtype=float))
+        noise_level_valid = self._validate_noise_level(noise_level, len(y))
+        self.n_last_appended = len(y)
+        self.X_train_all = np.append(self.X_train_all, X, axis=0)
+        self.y_train_all = np.append(self.y_train_all, y)
+        self._update_noise_level(noise_level_valid)
+        if self.infinities_classifier is None:
+            is_finite_all = np.full(fill_value=True, shape=(len(self.y_train_all),))
+            X_finite = np.copy(self.X_train_all)
+            y_finite = np.copy(self.y_train_all)
+        else:
+            diff_threshold_keep_n = self._diff_threshold_if_keep_n_finite(
+                self.y_train_all, self.keep_min_finite, self._diff_threshold)
+            is_finite_all = self.infinities_classifier._is_finite_raw(
+                self.y_train_all, diff_threshold_keep_n)
+            X_finite = np.copy(self.X_train_all[is_finite_all])
+            y_finite = np.copy(self.y_train_all[is_finite_all])
+        if fit_preprocessors:
+            self.preprocessing_X.fit(X_finite, y_finite)
+            self.preprocessing_y.fit(X_finite, y_finite)
+        self.X_train_all_ = self.preprocessing_X.transform(self.X_train_all)
+        self.y_train_all_ = self.preprocessing_y.transform(self.y_train_all)
+        noise_level_array = (
+            np.full(fill_value=self.noise_level, shape=(len(self.y_train_all_),))
+            if isinstance(self.noise_level, Number) else self.noise_level)
+        self.noise_level_ = self.preprocessing_y.transform_scale(noise_level_array)
+        if self.infinities_classifier is None:
+            is_finite_last_appended = np.full(fill_value=True, shape=(self.n_last_appended,))
+        else:
+            if fit_classifier:
+                diff_threshold_keep_n_ = self.preprocessing_y.transform_scale(
+                    diff_threshold_keep_n)
+                is_finite_predict = self.infinities_classifier.fit(
+                    self.X_train_all_, self.y_train_all_, diff_threshold_keep_n_)
+                assert np.array_equal(is_finite_all, is_finite_predict), \
+                    "Infinities classifier miss-classified at least 1 point."
+            is_finite_last_appended = is_finite_all[-self.n_last_appended:] \
+                if self.n_last_appended else is_finite_all[:0]
+        self.n_last_appended_finite = int(sum(is_finite_last_appended))
+        if not self.n_last_appended_finite and not force_fit_gpr:
+            return self
+        self.X_train = X_finite
+        self.y_train = y_finite
+        self.X_train_ = self.preprocessing_X.transform(self.X_train)
+        self.y_train_ = self.preprocessing_y.transform(self.y_train)
+        self.alpha = self.noise_level_[is_finite_all] ** 2
+        self.newly_appended_for_inv = self.n_last_appended_finite
+        self._dev_dirty = True
+        if fit_gpr:
+            self.fit_gpr_hyperparameters(**fit_gpr_kwargs)
+        else:
+            self._update_model()
+        self.update_trust_region()
+        return self
+
+    # ------------------------------------------------------------------ kernel plumbing
+    def _kernel_spec(self, kernel=None):
+        kernel = self.kernel_ if kernel is None else kernel
+        if not kernel.theta_is_standard(self.d):
+            raise NotImplementedError(
+                "the B200 path needs theta = [log c, log l_1..l_d] (free constant, free "
+                "anisotropic length scales), as GPry's auto-constructed kernels have")
+        return kernel.device_spec(self.d)
+
+    # ------------------------------------------------------------------ LML + fit
+    def log_marginal_likelihood(self, theta=None, eval_gradient=False, clone_kernel=True):
+        """gpr.py:876-881 -> sklearn _gpr.py:541-656, evaluated by gpry_lml_batched."""
+        self.n_eval_loglike += 1
+        if theta is None:
+            if eval_gradient:
+                raise ValueError("Gradient can only be evaluated for theta!=None")
+            return self.log_marginal_likelihood_value_
+        theta = np.asarray(theta, dtype=float)
+        if clone_kernel:
+            kernel = self.kernel_.clone_with_theta(theta)
+        else:
+            kernel = self.kernel_
+            kernel.theta = theta
+        kind, _, _ = self._kernel_spec(kernel)
+        lml, grad, info = workspace(self.device).lml_batched(
+            kind, self.X_train_, self.alpha, self.y_train_, theta[None, :],
+            eval_gradient=eval_gradient)
+        if eval_gradient:
+            return float(lml[0]), grad[0]
+        return float(lml[0])
+
+    def log_marginal_likelihood_batch(self, thetas, eval_gradient=True):
+        """LML (and gradient) for several theta at once (one device call; evaluations overlap
+        on the GPU).  Counts ``len(thetas)`` evaluations.  Does not touch ``kernel_``."""
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=float))
+        self.n_eval_loglike += len(thetas)
+        kind, _, _ = self._kernel_spec()
+        lml, grad, info = workspace(self.device).lml_batched(
+            kind, self.X_train_, self.alpha, self.y_train_, thetas, eval_gradient=eval_gradient)
+        return (lml, grad) if eval_gradient else lml
+
+    def fit_gpr_hyperparameters(self, simple=False, start_from_current=True, n_restarts=None,
+                                hyperparameter_bounds=None, lockstep=True):
+        """gpr.py:883-994.  Same restarts, same starting points (``rng.uniform`` over the
+        log-bounds in loop order), same scipy L-BFGS-B driver per restart.  With
+        ``lockstep=True`` (default) the restarts advance together and every round of
+        objective evaluations is ONE batched device call; each restart still sees exactly
+        the function values it would see alone, so the optimum is the same."""
+        if simple:
+            start_from_current = True
+            n_restarts = 1
+        if not self._fitted:
+            start_from_current = False
+        if n_restarts is None:
+            n_restarts = self.n_restarts_optimizer
+        if self.kernel_ is None:
+            self.kernel_ = deepcopy(self.kernel)
+        no_optimizer = self.optimizer is None
+        no_hyperparams = self.kernel.n_dims == 0
+        no_restarts = n_restarts <= 0
+        if no_optimizer or no_hyperparams or no_restarts:
+            reasons = []
+            if no_optimizer:
+                reasons += ["no optimizer has been specified"]
+            if no_hyperparams:
+                reasons += ["the kernel has no hyperparamenters"]
+            if no_restarts:
+                reasons += ["the number of optimizer restarts requested is 0."]
+            warnings.warn(f"Hyper-parameters not (re)fit. Reason(s): {'; '.join(reasons)}.")
+            self.log_marginal_likelihood_value_ = self.log_marginal_likelihood(
+                self.kernel_.theta, clone_kernel=False)
+            self._update_model()
+            return self
+        if hyperparameter_bounds is None:
+            hyperparameter_bounds = self.kernel_.bounds
+        if n_restarts - int(start_from_current):
+            if not np.isfinite(hyperparameter_bounds).all():
+                raise ValueError("There is at least one optimizer run the requires sampling "
+                                 "from the hyperparameters' prior, but it has not finite "
+                                 "density, because not all bounds are finite.")
+        self._rng = check_random_state(self.random_state)
+        theta_initials = []
+        for iteration in range(n_restarts):
+            if iteration == 0 and start_from_current:
+                theta_initials.append(np.array(self.kernel_.theta))
+            else:
+                theta_initials.append(self._rng.uniform(hyperparameter_bounds[:, 0],
+                                                        hyperparameter_bounds[:, 1]))
+        if lockstep and n_restarts > 1 and self.optimizer == "fmin_l_bfgs_b":
+            optima = self._lockstep_optimization(theta_initials, hyperparameter_bounds)
+        else:
+            def obj_func(theta, eval_gradient=True):
+                if eval_gradient:
+                    lml, grad = self.log_marginal_likelihood(theta, eval_gradient=True,
+                                                             clone_kernel=False)
+                    return -lml, -grad
+                return -self.log_marginal_likelihood(theta, clone_kernel=False)
+            optima = [self._constrained_optimization(obj_func, th0, hyperparameter_bounds)
+                      for th0 in theta_initials]
+        lml_values = list(map(itemgetter(1), optima))
+        self.log_marginal_likelihood_value_ = -np.min(lml_values)
+        self.kernel_.theta = optima[np.argmin(lml_values)][0]
+        self.newly_appended_for_inv = max(self.newly_appended_for_inv, 1)
+        self._update_model()
+        self._fitted = True
+        return self
+
+    def _constrained_optimization(self, obj_func, initial_theta, bounds):
+        """gpr.py:1435-1451."""
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if self.optimizer == "fmin_l_bfgs_b":
+                opt_res = scipy.optimize.minimize(obj_func, initial_theta, method="L-BFGS-B",
+                                                  jac=True, bounds=bounds)
+                return opt_res.x, opt_res.fun
+            if callable(self.optimizer):
+                return self.optimizer(obj_func, initial_theta, bounds=bounds)
+            raise ValueError("Unknown optimizer %s." % self.optimizer)
+
+    def _lockstep_optimization(self, theta_initials, bounds):
+        """Runs one scipy L-BFGS-B per restart in its own thread; their objective calls meet
+        at a barrier and are evaluated together by ``log_marginal_likelihood_batch``."""
+        n = len(theta_initials)
+        cond = threading.Condition()
+        pending = {}          # restart -> theta waiting for evaluation
+        results = {}          # restart -> (f, g)
+        active = set(range(n))
+        optima = [None] * n
+        errors = []
+
+        def flush_locked():
+            idx = sorted(pending)
+            thetas = np.array([pending[i] for i in idx])
+            lml, grad = self.log_marginal_likelihood_batch(thetas, eval_gradient=True)
+            for j, i in enumerate(idx):
+                results[i] = (-lml[j], -grad[j])
+            pending.clear()
+            cond.notify_all()
+
+        def obj(i):
+            def f(theta):
+                with cond:
+                    pending[i] = np.array(theta, dtype=float)
+                    if len(pending) == len(active):
+                        flush_locked()
+                    else:
+                        while i not in results:
+                            cond.wait()
+                    return results.pop(i)
+            return f
+
+        def run(i):
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    res = scipy.optimize.minimize(obj(i), theta_initials[i], method="L-BFGS-B",
+                                                  jac=True, bounds=bounds)
+                optima[i] = (res.x, res.fun)
+            except Exception as excpt:  # pragma: no cover
+                errors.append(excpt)
+            finally:
+                with cond:
+                    active.discard(i)
+                    if pending and len(pending) == len(active):
+                        flush_locked()
+
+        threads = [threading.Thread(target=run, args=(i,)) for i in range(n)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return optima
+
+    # ------------------------------------------------------------------ model update
+    def _update_model(self):
+        """gpr.py:996-1020: K = k(X_,X_) + diag(alpha); Cholesky; L^-1; alpha_ (on the GPU)."""
+        if self.newly_appended_for_inv < 1:
+            warnings.warn("No new points have been appended to the model.")
+            return self
+        self._kernel_inverse()
+        self.newly_appended_for_inv = 0
+        return self
+
+    def _kernel_inverse(self, kernel=None):
+        """gpr.py:1453-1465.  The reference receives the assembled matrix; here the kernel
+        matrix is built on the device from ``kernel_``, so the argument is ignored."""
+        kind, _, _ = self._kernel_spec()
+        N = len(self.y_train_)
+        L, V, alpha_, _, info = workspace(self.device).factorize(
+            kind, self.X_train_, np.broadcast_to(self.alpha, (N,)), self.y_train_,
+            self.kernel_.theta)
+        if info != 0:
+            raise np.linalg.LinAlgError(
+                "The kernel, %s, is not returning a positive definite matrix. Try gradually "
+                "increasing the 'noise_level' parameter of your GaussianProcessRegressor "
+                "estimator." % self.kernel_,
+                f"{info}-th leading minor of the array is not positive definite")
+        self.L_, self.V_, self.alpha_ = L, V, alpha_
+        self._dev_dirty = True
+
+    # ------------------------------------------------------------------ device state
+    def _device_state(self):
+        """Uploads (lazily, once per model change) what predict needs."""
+        if self._dev is None:
+            self._dev = DeviceGP(self.device)
+            self._dev_dirty = True
+        if self._dev_dirty:
+            kind, c, ell = self._kernel_spec()
+            px, py = self.preprocessing_X, self.preprocessing_y
+            if hasattr(px, "bounds_min"):
+                x_min, x_width = px.bounds_min, px.bounds_max - px.bounds_min
+            elif px is DummyPreprocessor or isinstance(px, DummyPreprocessor):
+                x_min = x_width = None
+            else:
+                raise NotImplementedError("X pre-processor must be Normalize_bounds or None")
+            if hasattr(py, "mean_"):
+                y_mean, y_std = py.mean_, py.std_
+            elif py is DummyPreprocessor or isinstance(py, DummyPreprocessor):
+                y_mean, y_std = 0.0, 1.0
+            else:
+                raise NotImplementedError("y pre-processor must be Normalize_y or None")
+            clip_hi = np.inf
+            if self.clip_factor is not None:   # gpr.py:1187-1195
+                clip_hi = (self.clip_factor * max(self.y_train)
+                           - (self.clip_factor - 1) * min(self.y_train))
+            self._dev.upload(kind, self.X_train_, self.alpha_, self.V_, c, ell, x_min, x_width,
+                             y_mean, y_std, clip_hi)
+            self._dev_dirty = False
+        return self._dev
+
+    # ------------------------------------------------------------------ predict
+    @staticmethod
+    def _as_2d(X, validate):
+        if validate:
+            X = np.asarray(X, dtype=float)
+            if X.ndim != 2:
+                raise ValueError(f"Expected 2D array, got {X.ndim}D array instead")
+            if not np.all(np.isfinite(X)):
+                raise ValueError("Input contains NaN or infinity")
+        return X
+
+    def predict(self, X, return_std=False, return_cov=False, return_mean_grad=False,
+                return_std_grad=False, validate=True, ignore_trust_region=False):
+        """gpr.py:1022-1273."""
+        self.n_eval += len(X)
+        if return_cov:
+            raise NotImplementedError("return_cov is not part of the B200 path")
+        if return_std_grad and not (return_std and return_mean_grad):
+            raise ValueError("Not returning std_gradient without returning the std and the "
+                             "mean grad.")
+        if X.shape[0] != 1 and (return_mean_grad or return_std_grad):
+            raise ValueError("Mean grad and std grad not implemented for n_samples > 1")
+        if return_std_grad:
+            raise NotImplementedError(
+                "return_std_grad (BatchOptimizer path, gpr.py:1247-1266) is not on the B200 "
+                "hot path yet; see DESIGN.md 'next rows'")
+        X = self._as_2d(X, validate)
+        impose_trust_region = self.trust_bounds is not None and not ignore_trust_region
+        i_outside_trust = None
+        if impose_trust_region:
+            i_outside_trust = np.logical_not(is_in_bounds(X, self.trust_bounds))
+        finite = None
+        if self.infinities_classifier is not None:   # gpr.py:1136-1174
+            X = np.copy(X)
+            n_samples, n_dims = X.shape
+            y_mean_full = np.ones(n_samples)
+            y_std_full = np.zeros(n_samples)
+            grad_mean_full = np.ones((n_samples, n_dims))
+            X_ = self.preprocessing_X.transform(X)
+            finite = self.infinities_classifier.predict(np.ascontiguousarray(X_),
+                                                        validate=validate)
+            if np.all(~finite):
+                y_mean = y_mean_full * self.minus_inf_value
+                out = [y_mean]
+                if return_std:
+                    out.append(np.zeros(n_samples))
+                if return_mean_grad:
+                    out.append(np.ones((n_samples, n_dims)) * self.inf_value)
+                return out[0] if len(out) == 1 else tuple(out)
+            y_mean_full[~finite] = self.minus_inf_value
+            grad_mean_full[~finite] = self.inf_value
+            X = X[finite]
+        dev = self._device_state()
+        y_mean, y_std = dev.predict(X, return_mean=True, return_std=return_std)
+        if finite is not None:
+            y_mean_full[finite] = y_mean
+            y_mean = y_mean_full
+        if impose_trust_region:
+            y_mean[i_outside_trust] = self.minus_inf_value
+        if return_std:
+            if finite is not None:
+                y_std_full[finite] = y_std
+                y_std = y_std_full
+            if not return_mean_grad:
+                return y_mean, y_std
+        if return_mean_grad:
+            grad_mean = dev.mean_grad(X[0])
+            if finite is not None:
+                grad_mean_full[finite] = grad_mean
+                grad_mean = grad_mean_full
+            if return_std:
+                return y_mean, y_std, grad_mean
+            return y_mean, grad_mean
+        return y_mean
+
+    def predict_std(self, X, validate=True):
+        """gpr.py:1275-1352 (no trust region)."""
+        self.n_eval += len(X)
+        X = self._as_2d(X, validate)
+        finite = None
+        if self.infinities_classifier is not None:
+            X = np.copy(X)
+            n_samples = X.shape[0]
+            y_std_full = np.zeros(n_samples)
+            X_ = self.preprocessing_X.transform(X)
+            finite = self.infinities_classifier.predict(np.ascontiguousarray(X_),
+                                                        validate=validate)
+            if np.all(~finite):
+                return np.zeros(n_samples)
+            X = X[finite]
+        _, y_std = self._device_state().predict(X, return_mean=False, return_std=True)
+        if finite is not None:
+            y_std_full[finite] = y_std
+            y_std = y_std_full
+        return y_std
+
+    # ------------------------------------------------------------------ fused fast paths
+    def predict_logexp(self, X, zeta, noise_level=None, stream=None):
+        """mean, std and LogExp acquisition in one device pass (NORA's scoring,
+        mpi.py:182-218 + gp_acquisition.py:1049-1051, 1123-1124).  No classifier / trust
+        region masks are applied (as in ``LogExp.f``); counts ``len(X)`` evaluations."""
+        self.n_eval += len(X)
+        noise_level = self.noise_level if noise_level is None else noise_level
+        if np.iterable(noise_level):
+            noise_level = float(np.mean(noise_level))
+        return self._device_state().predict_logexp(X, zeta, noise_level, self.y_max,
+                                                   stream=stream)
+
+    def predict_logexp_topk(self, X, zeta, Kp, noise_level=None, idx_offset=0, stream=None,
+                            device_out=False, want_X=True):
+        """Fused scoring + descending-acquisition pre-ranking: only the Kp best candidates
+        leave the GPU.  Returns (acq, idx, mean, std, X)."""
+        self.n_eval += len(X)
+        noise_level = self.noise_level if noise_level is None else noise_level
+        if np.iterable(noise_level):
+            noise_level = float(np.mean(noise_level))
+        return self._device_state().predict_logexp_topk(
+            X, zeta, noise_level, self.y_max, Kp, idx_offset=idx_offset, stream=stream,
+            device_out=device_out, want_X=want_X)

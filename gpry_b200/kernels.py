@@ -250,6 +250,25 @@ class Product(Kernel):
         """True if theta is exactly [log c, log l_1..l_d] (nothing fixed, anisotropic)."""
         return self.theta.shape[0] == d + 1 and isinstance(self.k1, ConstantKernel)
 
+    def __call__(self, X, Y=None, eval_gradient=False):
+        """k(X, Y) evaluated on the GPU (Product.__call__, sklearn:kernels.py:971).  The
+        (N, N, 1+d) theta-gradient tensor is never built by this package: use
+        ``GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True)``."""
+        if eval_gradient:
+            raise NotImplementedError(
+                "dK/dtheta is fused into the log-marginal-likelihood kernel on the device and "
+                "never materialised")
+        from .device import workspace
+        from .gpr import default_device
+        X = np.atleast_2d(np.asarray(X, dtype=float))
+        d = X.shape[1]
+        kind, c, ell = self.device_spec(d)
+        theta = np.log(np.concatenate([[c], ell]))
+        K = workspace(default_device()).kernel_cross(kind, theta, X, X if Y is None else Y)
+        if Y is None:
+            np.fill_diagonal(K, c)   # pdist/squareform path: unit diagonal times c (:1566)
+        return K
+
     def diag(self, X):
         """k(x, x) = c (sklearn:kernels.py:973-990, 1298-1322)."""
         kind, c, _ = self.device_spec(np.atleast_2d(X).shape[1])

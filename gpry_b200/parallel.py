@@ -1,0 +1,190 @@
+"""
+Process-level parallel helpers with the interface of ``gpry.mpi`` (reference mpi.py), on top
+of ``torch.distributed`` (one process per GPU; NCCL between GPUs over NVLink, gloo for the
+CPU-only tests) instead of mpi4py.  Without an initialised process group everything degrades
+to the serial behaviour, exactly like the reference's mpi4py-less fallbacks (mpi.py:18-28).
+
+What is sharded: candidates by stride ``[RANK::SIZE]``
+(``step_split``, mpi.py:105-115) with the training state replicated; hyper-parameter restarts
+by ``split_number_for_parallel_processes`` (mpi.py:80-102).  The only exchange steps are the
+gather of per-rank predictions (``merge_step_split``, mpi.py:118-131), the all-gather of the
+per-GPU survivor lists of the ranked pool, and the all-gather of (lml, theta) after a fit.
+"""
+import numpy as np
+
+try:
+    import torch
+    import torch.distributed as dist
+except ImportError:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def _on():
+    return dist is not None and dist.is_available() and dist.is_initialized()
+
+
+def size():
+    return dist.get_world_size() if _on() else 1
+
+
+def rank():
+    return dist.get_rank() if _on() else 0
+
+
+def is_main_process():
+    return rank() == 0
+
+
+def multiple_processes():
+    return size() > 1
+
+
+def _device():
+    """Tensor device for collectives: the rank's GPU under NCCL, CPU under gloo."""
+    if _on() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def bcast(obj, root=0):
+    """mpi.py:53-59."""
+    if not multiple_processes():
+        return obj
+    box = [obj if rank() == root else None]
+    dist.broadcast_object_list(box, src=root)
+    return box[0]
+
+
+def allgather(obj):
+    """mpi.py:71-77."""
+    if not multiple_processes():
+        return [obj]
+    out = [None] * size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def gather(obj, root=0):
+    """mpi.py:62-68 (every rank gets the list; only ``root`` is meant to use it)."""
+    out = allgather(obj)
+    return out if rank() == root else None
+
+
+def sync_processes():
+    if multiple_processes():
+        dist.barrier()
+
+
+def split_number_for_parallel_processes(n, n_proc=None):
+    """mpi.py:80-102: 5 tasks on 3 processes -> [2, 2, 1]."""
+    n_proc = size() if n_proc is None else n_proc
+    n_rounded = int(np.ceil(n / n_proc)) * n_proc
+    slots = np.zeros(n_rounded, dtype=int)
+    slots[:n] = 1
+    return np.sum(slots.reshape((n_rounded // n_proc, n_proc)), axis=0)
+
+
+def step_split(values, root=0):
+    """mpi.py:105-115: broadcast from rank 0, keep ``values[RANK::SIZE]``."""
+    if not multiple_processes():
+        return values
+    values = bcast(values, root=root)
+    return values[rank()::size()]
+
+
+def merge_step_split(values):
+    """mpi.py:118-131: inverse of ``step_split`` on rank 0 (``None`` elsewhere)."""
+    if not multiple_processes():
+        return values
+    parts = allgather(values)
+    if not is_main_process():
+        return None
+    merged = np.zeros(sum(len(v) for v in parts))
+    for i, v in enumerate(parts):
+        merged[i::size()] = v
+    return merged
+
+
+def compute_y_parallel(gpr, X, y, sigma_y, ensure_sigma_y=False):
+    """mpi.py:182-218: GP mean (and std) of a sample held by rank 0, computed by all ranks on
+    their strided shard (each on its own GPU) and merged on rank 0."""
+    y = bcast(y)
+    if y is None:
+        this_X = step_split(X)
+        if len(this_X) > 0:
+            if ensure_sigma_y:
+                this_y, this_sigma = gpr.predict(this_X, return_std=True, validate=False)
+            else:
+                this_y, this_sigma = gpr.predict(this_X, return_std=False, validate=False), None
+        else:
+            this_y = np.array([], dtype=float)
+            this_sigma = np.array([], dtype=float) if ensure_sigma_y else None
+        return (merge_step_split(this_y),
+                merge_step_split(this_sigma) if ensure_sigma_y else None)
+    sigma_y = bcast(sigma_y)
+    if sigma_y is None and ensure_sigma_y:
+        this_X = step_split(X)
+        this_sigma = gpr.predict_std(this_X, validate=False) if len(this_X) > 0 \
+            else np.array([], dtype=float)
+        return (y if is_main_process() else None, merge_step_split(this_sigma))
+    return (y, sigma_y) if is_main_process() else (None, None)
+
+
+# ---------------------------------------------------------------------------------------
+# exchange steps of the ranked pool / restart-parallel fit (tensor collectives)
+# ---------------------------------------------------------------------------------------
+def max_scalar(x):
+    if not multiple_processes():
+        return float(x)
+    t = torch.tensor([float(x)], dtype=torch.float64, device=_device())
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def any_true(flag):
+    return max_scalar(1.0 if flag else 0.0) > 0.0
+
+
+def allgather_survivors(acq, idx, mean, std, X):
+    """All-gather of the per-rank survivor records (acq, idx, mean, std, X[K', d]) so that every
+    rank holds the union (replaces gp_acquisition.py:1148-1171 + bcast :1190).  Ragged counts
+    are handled by padding to the largest K'."""
+    if not multiple_processes():
+        return acq, idx, mean, std, X
+    dev = _device()
+    d = X.shape[1]
+    n = len(acq)
+    counts = torch.zeros(size(), dtype=torch.int64, device=dev)
+    counts[rank()] = n
+    dist.all_reduce(counts)
+    nmax = int(counts.max().item())
+    rec = torch.zeros((nmax, 4 + d), dtype=torch.float64, device=dev)
+    if n:
+        host = np.empty((n, 4 + d))
+        host[:, 0], host[:, 1], host[:, 2], host[:, 3] = acq, idx.astype(np.float64), mean, std
+        host[:, 4:] = X
+        rec[:n] = torch.from_numpy(host).to(dev)
+    out = torch.empty(size() * nmax * (4 + d), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, rec.view(-1))
+    out = out.cpu().numpy().reshape(size(), nmax, 4 + d)
+    parts = [out[r, :int(counts[r].item())] for r in range(size())]
+    allrec = np.concatenate(parts, axis=0)
+    return (allrec[:, 0].copy(), allrec[:, 1].astype(np.int64), allrec[:, 2].copy(),
+            allrec[:, 3].copy(), np.ascontiguousarray(allrec[:, 4:]))
+
+
+def best_fit_across_processes(lml, theta):
+    """run.py:1286-1293: all-gather (lml, theta) of every rank's best restart; every rank
+    returns the global best (ties -> lowest rank), so no pickled regressor has to travel: the
+    winner is re-factorised locally from theta."""
+    if not multiple_processes():
+        return lml, np.asarray(theta), 0
+    dev = _device()
+    rec = torch.tensor(np.concatenate([[lml], np.asarray(theta, dtype=float)]),
+                       dtype=torch.float64, device=dev)
+    out = torch.empty(size() * rec.numel(), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, rec)
+    out = out.cpu().numpy().reshape(size(), -1)
+    best = int(np.argmax(out[:, 0]))
+    return float(out[best, 0]), out[best, 1:].copy(), best

@@ -136,6 +136,26 @@ int gpry_topk(gpry_state* st, const double* scores, int64_t M, int Kp, int where
 int gpry_mean_grad(gpry_state* st, const double* x, double* out_grad);
 
 /*
+ * Posterior covariance (normalised units, prior variance c on the diagonal minus the explained
+ * part, NO noise term) among Ka <= 8192 candidates X (Ka x d, un-transformed):
+ *   Sigma = k(Xa, Xa) - (V K*a^T)^T (V K*a^T),   out_cov: Ka x Ka row major.
+ * This is what RankedPool's Kriging-believer conditioning (gp_acquisition.py:1464-1494,
+ * 1522-1555, 1598-1670: deepcopy + append_to_data + O((N+i)^3) refit per cached model) needs:
+ * var(a | pool P) = Sigma_aa - Sigma_aP (Sigma_PP + noise2 I)^-1 Sigma_Pa.
+ */
+int gpry_posterior_cov(gpry_state* st, const double* X, int Ka, int where, double* out_cov,
+                       void* stream);
+
+/* k_theta(X, Y) for already-transformed host arrays X (M x d), Y (N x d) -> out (M x N):
+ * Product.__call__ (sklearn:kernels.py:971).  API completeness; needs no uploaded model. */
+int gpry_kernel_cross(gpry_state* st, int kind, int d, const double* theta, const double* X,
+                      int M, const double* Y, int N, double* out);
+
+/* d k(x, X_train_) / d x_ at one TRANSFORMED point x_t (d) -> out (N x d):
+ * Kernel.gradient_x (kernels.py:257-278, 363-432, 687-699) of the uploaded model. */
+int gpry_kernel_gradient_x(gpry_state* st, const double* x_t, double* out);
+
+/*
  * K = k_theta(X_, X_) + diag(noise2); L = chol(K); V = L^-1; alpha_ = K^-1 y_.
  * theta = [log c, log ell_1..ell_d].  Host pointers; out_L / out_V (N x N row major, lower,
  * upper triangle zeroed) and out_alpha (N) may be NULL.  *info = 0 or the order of the

@@ -144,6 +144,33 @@ def nonpd_case(gpry):
     print("lml_nonpd:", v, g)
 
 
+def fit_case(gpry):
+    """Reference hyper-parameter fit (gpr.py:883-994): 4 restarts from a seeded RandomState."""
+    from gpry.preprocessing import Normalize_bounds, Normalize_y
+    rng = np.random.default_rng(21)
+    d, N = 2, 40
+    bounds = np.array([[0.0, 1.0]] * d)
+    X = rng.uniform(size=(N, d))
+    y = target(X)
+    import warnings
+    gpr = gpry.gpr.GaussianProcessRegressor(
+        kernel="RBF", bounds=bounds, noise_level=1e-2, n_restarts_optimizer=4,
+        preprocessing_X=Normalize_bounds(bounds), preprocessing_y=Normalize_y(),
+        account_for_inf=None, random_state=7, verbose=0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gpr.append_to_data(X, y, fit_gpr=True)
+    Xc = rng.uniform(size=(64, d))
+    mean, std = gpr.predict(Xc, return_std=True, validate=False)
+    np.savez_compressed(os.path.join(OUT, "fit_rbf_d2_n40.npz"), X_train=X, y_train=y,
+                        bounds=bounds, theta_opt=gpr.kernel_.theta,
+                        lml_opt=gpr.log_marginal_likelihood_value_,
+                        n_eval_loglike=gpr.n_eval_loglike, Xc=Xc, mean=mean, std=std,
+                        kernel_bounds=gpr.kernel_.bounds, theta_init=gpr.kernel.theta)
+    print("fit_rbf_d2_n40: theta_opt", gpr.kernel_.theta, "lml", gpr.log_marginal_likelihood_value_,
+          "n_eval_loglike", gpr.n_eval_loglike)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gpry = import_reference()
@@ -157,6 +184,7 @@ def main():
     case(gpry, "rbf_d8_n1000", "rbf", 1000, 8, 512, 1234, 0.5, with_lml=False,
          store_train=False)
     nonpd_case(gpry)
+    fit_case(gpry)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,156 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares;
+host-side logic (kernel descriptors, pre-processors, ranked pool control flow, NORA
+pre-selection bound) behaves like the reference.  No compute call touches a GPU here."""
+import os
+import re
+from copy import deepcopy
+from functools import partial
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_pool_candidates, load_golden, oracle_state
+from oracle import gp_oracle as orc
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "gpry_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gpry_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    import ctypes
+    from gpry_b200 import _lib
+    lib = _lib.load_library()
+    names = header_functions()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.gpry_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    """Without a CUDA device the product path must raise, not fall back."""
+    from gpry_b200 import _lib
+    lib = _lib.load_library()
+    if lib.gpry_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    from gpry_b200 import DeviceGP, GpryB200Error
+    with pytest.raises(GpryB200Error):
+        DeviceGP(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gpry_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), fn
+
+
+def test_kernel_descriptors():
+    from gpry_b200.kernels import ConstantKernel as C, RBF, Matern
+    d = 3
+    k = C(10.0, [1e-4, 1e6]) * RBF([0.1] * d, [1e-3, 1e1], prior_bounds=np.array([[0, 1.]] * d))
+    assert np.allclose(k.theta, np.log([10.0, 0.1, 0.1, 0.1]))
+    assert np.allclose(k.bounds, np.log([[1e-4, 1e6]] + [[1e-3, 10.0]] * d))
+    k.theta = np.log([2.0, 0.5, 0.6, 0.7])
+    assert k.k1.constant_value == pytest.approx(2.0) and np.allclose(k.k2.length_scale,
+                                                                      [0.5, 0.6, 0.7])
+    assert k.device_spec(d)[0] == "rbf" and k.theta_is_standard(d)
+    k2 = k.clone_with_theta(np.log([1.0, 1.0, 1.0, 1.0]))
+    assert k.k1.constant_value == pytest.approx(2.0) and k2.k1.constant_value == 1.0
+    m = C(1.0) * Matern([1.0] * d, nu=2.5)
+    assert m.device_spec(d)[0] == "matern25"
+    with pytest.raises(ValueError):
+        Matern(nu=0.5)
+    dyn = RBF([0.2, 0.3], "dynamic", prior_bounds=np.array([[0, 2.], [0, 4.]]))
+    assert np.allclose(dyn.bounds, np.log([[2e-3, 200.], [4e-3, 400.]]))
+    assert len(k.hyperparameters) == 2 and k.hyperparameters[1].n_elements == d
+
+
+def test_preprocessing():
+    from gpry_b200.preprocessing import Normalize_bounds, Normalize_y
+    b = np.array([[-1.0, 3.0], [2.0, 2.5]])
+    nb = Normalize_bounds(b)
+    X = np.array([[0.0, 2.25], [3.0, 2.0]])
+    assert np.array_equal(nb.transform(X), orc.normalize_bounds_transform(X, b))
+    assert np.allclose(nb.inverse_transform(nb.transform(X)), X)
+    ny = Normalize_y()
+    y = np.array([1.0, -2.0, np.inf, 5.0])
+    ny.fit(None, y)
+    assert (ny.mean_, ny.std_) == orc.normalize_y_fit(y)
+    with pytest.raises(TypeError):
+        Normalize_y().transform(y)
+
+
+class OracleBackedGPR:
+    """A stand-in regressor (CPU oracle) with the few methods RankedPool's 'refit'
+    conditioning uses, to test the pool's control flow without a GPU."""
+
+    def __init__(self, st):
+        self.st = st
+        self.d = st.d
+        self.noise_level = st.noise_level
+        self.y_max = st.y_max
+
+    def predict_std(self, X, validate=True):
+        return orc.predict_std(self.st, X)
+
+    def append_to_data(self, X, y, fit_gpr=False, fit_classifier=False):
+        self.st = self.st.appended(X, y)
+
+    def __deepcopy__(self, memo):
+        return OracleBackedGPR(self.st)
+
+
+@pytest.mark.parametrize("name", ["rbf_d2_n60", "rbf_d8_n300"])
+@pytest.mark.parametrize("method", ["single sort acq", "bulk"])
+def test_ranked_pool_control_flow(name, method):
+    from gpry_b200.acquisition_functions import LogExp
+    from gpry_b200.gp_acquisition import RankedPool
+    g = load_golden(name)
+    st = oracle_state(g)
+    Xp = golden_pool_candidates(g)
+    y, sigma, acq = orc.predict_logexp(st, Xp, zeta=g["zeta"])
+    keep = np.argsort(acq)[::-1][:300]
+    acq_func = partial(LogExp.f, baseline=st.y_max, noise_level=st.noise_level, zeta=g["zeta"])
+    n_points = int(g["pool_n_points"])
+    pool = RankedPool(n_points, gpr=OracleBackedGPR(st), acq_func=acq_func, verbose=0)
+    with np.errstate(divide="ignore"):
+        pool.add(Xp[keep], y[keep], sigma[keep], acq[keep], method=method)
+    tag = method.replace(" ", "_")
+    assert np.array_equal(keep[pool.idx[:n_points]], g[f"pool_idx_{tag}"])
+    assert acq[keep][-1] <= pool.min_acq
+    c = pool.copy(drop_empty=True)
+    assert len(c.y) == n_points + 1 and not hasattr(c, "_gpr")
+    # LogExp.f is the reference's static formula
+    mu, s = np.array([1.0, 2.0]), np.array([0.5, 0.005])
+    with np.errstate(divide="ignore"):
+        v = LogExp.f(mu, s, 3.0, 0.01, 0.3)
+    assert v[0] == pytest.approx(2 * 0.3 * (1 - 3) + 0.5 * np.log(0.25 - 1e-4)) and v[1] == -np.inf
+
+
+def test_gpr_host_logic_without_gpu():
+    """Constructor, kernel auto-construction and argument checks need no device."""
+    from gpry_b200.gpr import GaussianProcessRegressor
+    from gpry_b200.preprocessing import Normalize_bounds, Normalize_y
+    bounds = np.array([[0.0, 1.0]] * 4)
+    gpr = GaussianProcessRegressor(kernel={"Matern": {"nu": 2.5}}, bounds=bounds,
+                                   preprocessing_X=Normalize_bounds(bounds),
+                                   preprocessing_y=Normalize_y(), verbose=0)
+    assert gpr.d == 4 and gpr.n == 0 and not gpr.fitted
+    assert repr(gpr.kernel).startswith("3.16**2 * Matern(")
+    assert np.allclose(gpr.kernel.theta, np.log([10.0] + [0.1] * 4))       # gpr.py:351-352
+    assert np.allclose(gpr.kernel.bounds, np.log([[1e-4, 1e6]] + [[1e-3, 10.0]] * 4))
+    with pytest.raises(ValueError):
+        GaussianProcessRegressor(kernel="Foo", bounds=bounds)
+    with pytest.raises(ValueError):
+        GaussianProcessRegressor(bounds=bounds, clip_factor=0.5)
+    import pickle
+    g2 = pickle.loads(pickle.dumps(gpr))
+    assert g2._dev is None and g2.d == 4
+    assert deepcopy(gpr).kernel == gpr.kernel

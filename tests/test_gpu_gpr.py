@@ -1,0 +1,190 @@
+"""GPU tests of the reference-shaped Python layer (gpry_b200.gpr / acquisition_functions /
+gp_acquisition) against golden vectors from the real reference: they read like tests of
+``gpry.gpr.GaussianProcessRegressor`` itself."""
+import os
+import pickle
+from copy import deepcopy
+from functools import partial
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, golden_pool_candidates, load_golden, scaled_err
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def make_gpr(g, **kw):
+    from gpry_b200.gpr import GaussianProcessRegressor
+    from gpry_b200.preprocessing import Normalize_bounds, Normalize_y
+    kernel = {"rbf": "RBF", "matern15": {"Matern": {"nu": 1.5}},
+              "matern25": {"Matern": {"nu": 2.5}}}[g["kind"]]
+    norm = g["normalize"]
+    gpr = GaussianProcessRegressor(
+        kernel=kernel, bounds=g["bounds"], noise_level=g["noise_level"],
+        preprocessing_X=Normalize_bounds(g["bounds"]) if norm else None,
+        preprocessing_y=Normalize_y() if norm else None, account_for_inf=None, verbose=0, **kw)
+    gpr.kernel_ = deepcopy(gpr.kernel)
+    gpr.kernel_.theta = g["theta"]
+    gpr.append_to_data(g["X_train"], g["y_train"], fit_gpr=False)
+    return gpr
+
+
+def test_predict_like_reference(golden):
+    g = golden
+    gpr = make_gpr(g)
+    sy = float(g["y_std"])
+    n0 = gpr.n_eval
+    mean, std = gpr.predict(g["Xc"], return_std=True, validate=False)
+    assert gpr.n_eval == n0 + len(g["Xc"])
+    assert scaled_err(mean, g["mean"], sy) < TOL
+    assert scaled_err(std ** 2, g["std"] ** 2, sy ** 2) < TOL
+    assert scaled_err(gpr.predict(g["Xc"]), g["mean_only"], sy) < TOL
+    assert scaled_err(gpr.predict_std(g["Xc"]) ** 2, g["std_only"] ** 2, sy ** 2) < TOL
+    m1, s1, gm = gpr.predict(g["Xc"][:1], return_std=True, return_mean_grad=True)
+    assert scaled_err(gm, g["grad_mean"], np.abs(g["grad_mean"]).max()) < TOL
+    m1b, gmb = gpr.predict(g["Xc"][:1], return_mean_grad=True)
+    assert np.array_equal(gm, gmb) and m1b[0] == m1[0]
+    # fitted attributes are numpy arrays like the reference's
+    N = g["N"]
+    assert gpr.V_.shape == (N, N) and gpr.L_.shape == (N, N) and gpr.alpha_.shape == (N,)
+    assert scaled_err(gpr.alpha_, g["alpha_"], np.abs(g["alpha_"]).max()) < TOL
+    assert abs(gpr.y_max - float(g["y_max"])) == 0
+
+
+def test_errors_like_reference(golden):
+    gpr = make_gpr(golden)
+    X = golden["Xc"]
+    with pytest.raises(ValueError):
+        gpr.predict(X[:1], return_std_grad=True)
+    with pytest.raises(ValueError):
+        gpr.predict(X[:2], return_mean_grad=True)
+
+
+def test_logexp_call(golden):
+    from gpry_b200.acquisition_functions import LogExp
+    g = golden
+    gpr = make_gpr(g)
+    acq = LogExp(zeta=g["zeta"])(g["Xc"], gpr)
+    ref = g["acq_call"]
+    var_ref = g["std"] ** 2 - g["noise_level"] ** 2
+    resolved = np.abs(var_ref) > 1e-6 * float(g["y_std"]) ** 2
+    assert np.array_equal(np.isfinite(acq)[resolved], np.isfinite(ref)[resolved])
+    ok = resolved & np.isfinite(ref)
+    assert scaled_err(acq[ok], ref[ok], 1.0) < 1e-9
+    assert LogExp(dimension=g["d"]).zeta == pytest.approx(g["zeta"], rel=1e-15)
+
+
+def test_lml_like_reference(golden):
+    g = golden
+    if "lml" not in g:
+        pytest.skip("no LML in this fixture")
+    gpr = make_gpr(g)
+    n0 = gpr.n_eval_loglike
+    for th, v, gr in zip(g["lml_thetas"], g["lml"], g["lml_grad"]):
+        lml, grad = gpr.log_marginal_likelihood(th, eval_gradient=True, clone_kernel=True)
+        assert abs(lml - v) < TOL * abs(v)
+        assert scaled_err(grad, gr, np.abs(gr).max()) < TOL
+    assert gpr.n_eval_loglike == n0 + 2
+    assert np.array_equal(gpr.kernel_.theta, g["theta"])          # clone_kernel=True
+    gpr.log_marginal_likelihood(g["lml_thetas"][1], clone_kernel=False)
+    assert np.allclose(gpr.kernel_.theta, g["lml_thetas"][1], rtol=1e-15)   # side effect
+
+
+def test_pickle_and_deepcopy(golden):
+    g = golden
+    gpr = make_gpr(g)
+    mean, std = gpr.predict(g["Xc"], return_std=True)
+    clone = pickle.loads(pickle.dumps(gpr))
+    m2, s2 = clone.predict(g["Xc"], return_std=True)
+    assert np.array_equal(mean, m2) and np.array_equal(std, s2)
+    dc = deepcopy(gpr)
+    assert dc._dev is None and dc.n_eval == gpr.n_eval
+    m3, s3 = dc.predict(g["Xc"], return_std=True)
+    assert np.array_equal(mean, m3) and np.array_equal(std, s3)
+    # a copy with appended lie points does not disturb the original
+    dc.append_to_data(g["Xc"][:3], mean[:3], fit_gpr=False, fit_classifier=False)
+    assert dc.n == gpr.n + 3
+    m4, s4 = gpr.predict(g["Xc"], return_std=True)
+    assert np.array_equal(mean, m4) and np.array_equal(std, s4)
+    assert np.all(dc.predict_std(g["Xc"][:3]) < std[:3])
+
+
+@pytest.mark.parametrize("conditioning", ["refit", "cov"])
+@pytest.mark.parametrize("method", ["single sort acq", "bulk"])
+def test_ranked_pool_like_reference(golden, method, conditioning):
+    from gpry_b200.acquisition_functions import LogExp
+    from gpry_b200.gp_acquisition import RankedPool
+    g = golden
+    if "pool_M" not in g:
+        pytest.skip("no ranked pool in this fixture")
+    gpr = make_gpr(g)
+    Xp = golden_pool_candidates(g)
+    y, sigma, acq = gpr.predict_logexp(Xp, g["zeta"])
+    assert scaled_err(np.sort(acq)[::-1][:64], g["pool_acq_top"], 1.0) < 1e-9
+    acq_func = partial(LogExp.f, baseline=gpr.y_max, noise_level=gpr.noise_level,
+                       zeta=g["zeta"])
+    n_points = int(g["pool_n_points"])
+    keep = np.argsort(acq)[::-1][:1024]      # pre-selected survivors (checked exact below)
+    pool = RankedPool(n_points, gpr=gpr, acq_func=acq_func, verbose=0,
+                      conditioning=conditioning)
+    with np.errstate(divide="ignore"):
+        pool.add(Xp[keep], y[keep], sigma[keep], acq[keep], method=method)
+    tag = method.replace(" ", "_")
+    assert acq[keep][-1] <= pool.min_acq          # pre-selection was exact
+    assert np.array_equal(keep[pool.idx[:n_points]], g[f"pool_idx_{tag}"])
+    assert scaled_err(pool.acq_cond[:n_points], g[f"pool_acq_cond_{tag}"], 1.0) < 1e-8
+
+
+def test_nora_multi_add(golden):
+    from gpry_b200.acquisition_functions import LogExp
+    from gpry_b200.gp_acquisition import NORA
+    g = golden
+    if "pool_M" not in g:
+        pytest.skip("no ranked pool in this fixture")
+    gpr = make_gpr(g)
+    Xp = golden_pool_candidates(g)
+    n_points = int(g["pool_n_points"])
+    nora = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=64)
+    X_pool, y_pool, acq_pool = nora.multi_add(gpr, n_points=n_points, X_mc=Xp)
+    ref_idx = g["pool_idx_single_sort_acq"]
+    assert np.array_equal(X_pool, Xp[ref_idx])
+    assert scaled_err(y_pool, g["pool_y_single_sort_acq"], float(g["y_std"])) < TOL
+    # a second call re-uses the sample and must not propose the same points again
+    X2, _, _ = nora.multi_add(gpr, n_points=n_points)
+    assert not set(map(bytes, X2)) & set(map(bytes, X_pool))
+
+
+def test_kernel_call(golden):
+    g = golden
+    gpr = make_gpr(g)
+    st_X = gpr.X_train_[:50]
+    K = gpr.kernel_(gpr.preprocessing_X.transform(g["Xc"][:20]), st_X)
+    Ko = orc.kernel_cross(g["kind"], g["theta"], gpr.preprocessing_X.transform(g["Xc"][:20]), st_X)
+    assert scaled_err(K, Ko, 1.0) < 1e-13
+    G = gpr._device_state().kernel_gradient_x(gpr.preprocessing_X.transform(g["Xc"][:1])[0])
+    Go = orc.kernel_gradient_x(g["kind"], g["theta"],
+                               gpr.preprocessing_X.transform(g["Xc"][:1])[0], gpr.X_train_)
+    assert scaled_err(G, Go, np.abs(Go).max()) < 1e-12
+
+
+def test_fit_like_reference():
+    from gpry_b200.gpr import GaussianProcessRegressor
+    from gpry_b200.preprocessing import Normalize_bounds, Normalize_y
+    z = np.load(os.path.join(GOLDEN_DIR, "fit_rbf_d2_n40.npz"))
+    for lockstep in (True, False):
+        gpr = GaussianProcessRegressor(
+            kernel="RBF", bounds=z["bounds"], noise_level=1e-2, n_restarts_optimizer=4,
+            preprocessing_X=Normalize_bounds(z["bounds"]), preprocessing_y=Normalize_y(),
+            account_for_inf=None, random_state=7, verbose=0)
+        assert np.allclose(gpr.kernel.theta, z["theta_init"], rtol=1e-15)
+        assert np.allclose(gpr.kernel.bounds, z["kernel_bounds"], rtol=1e-15)
+        gpr.append_to_data(z["X_train"], z["y_train"],
+                           fit_gpr={"n_restarts": 4, "lockstep": lockstep})
+        assert gpr.fitted
+        ref = float(z["lml_opt"])
+        assert gpr.log_marginal_likelihood_value_ >= ref - 1e-3 * abs(ref)
+        mean = gpr.predict(z["X_train"][:5])
+        assert np.allclose(mean, z["y_train"][:5], atol=1e-2 * np.std(z["y_train"]))

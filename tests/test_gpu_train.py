@@ -67,7 +67,8 @@ def test_lml_nonpd(dev):
 
 
 @pytest.mark.parametrize("kind,N,d", [("rbf", 1000, 8), ("matern25", 500, 6),
-                                      ("matern15", 129, 2), ("rbf", 2000, 12)])
+                                      ("matern15", 129, 2), ("rbf", 2000, 12), ("rbf", 203, 5),
+                                      ("matern25", 61, 3)])
 def test_oracle_lml(dev, kind, N, d):
     X, y, theta, bounds = orc.synthetic_problem(N, d)
     st = orc.GPState(kind, theta, X, y, bounds=bounds)

@@ -1,0 +1,130 @@
+"""world_size-2 tests (gloo, CPU) of the multi-process host logic: strided sharding and merge
+(mpi.py:105-131), restart split (mpi.py:80-102), survivor all-gather, best-fit selection and
+the sharded NORA ranking (result on 2 ranks == result on 1 rank)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, golden_pool_candidates, load_golden, oracle_state
+from oracle import gp_oracle as orc
+
+
+class FakeDeviceGPR:
+    """CPU stand-in (oracle arithmetic) exposing what NORA / parallel helpers call."""
+
+    class _PY:
+        def __init__(self, std_):
+            self.std_ = std_
+
+    def __init__(self, st):
+        self.st = st
+        self.d = st.d
+        self.noise_level = st.noise_level
+        self.y_max = st.y_max
+        self.preprocessing_y = self._PY(st.y_std)
+        self.n_eval = 0
+
+    def predict(self, X, return_std=False, validate=True):
+        self.n_eval += len(X)
+        return orc.predict(self.st, X, return_std=return_std)
+
+    def predict_std(self, X, validate=True):
+        return orc.predict_std(self.st, X)
+
+    def predict_logexp_topk(self, X, zeta, Kp, **kw):
+        m, s, a = orc.predict_logexp(self.st, X, zeta=zeta)
+        order = np.lexsort((np.arange(len(a)), -a))[:Kp]
+        return a[order], order.astype(np.int64), m[order], s[order], X[order]
+
+    def _device_state(self):
+        return self
+
+    def posterior_cov(self, X):
+        X_ = self.st.transform_X(X)
+        Ks = orc.kernel_cross(self.st.kind, self.st.theta, X_, self.st.X_train_)
+        U = self.st.V_ @ Ks.T
+        return orc.kernel_cross(self.st.kind, self.st.theta, X_, X_) - U.T @ U
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gpry_b200 import parallel
+    from gpry_b200.acquisition_functions import LogExp
+    from gpry_b200.gp_acquisition import NORA
+    res = {}
+    assert parallel.size() == world and parallel.rank() == rank
+    # strided split + merge round trip
+    vals = np.arange(11, dtype=float) if rank == 0 else None
+    mine = parallel.step_split(vals)
+    assert np.array_equal(mine, np.arange(11, dtype=float)[rank::world])
+    merged = parallel.merge_step_split(mine * 2)
+    if rank == 0:
+        assert np.array_equal(merged, 2 * np.arange(11, dtype=float))
+    else:
+        assert merged is None
+    assert list(parallel.split_number_for_parallel_processes(5, 3)) == [2, 2, 1]
+    assert list(parallel.split_number_for_parallel_processes(64, 8)) == [8] * 8
+    assert parallel.bcast("x" if rank == 0 else None) == "x"
+    assert parallel.allgather(rank) == list(range(world))
+    assert parallel.max_scalar(float(rank)) == world - 1
+    # ragged survivor all-gather
+    n = 3 + rank
+    a = np.arange(n, dtype=float) + 10 * rank
+    rec = parallel.allgather_survivors(a, np.arange(n) + 100 * rank, a + 0.5, a + 0.25,
+                                       np.outer(a, np.ones(2)))
+    assert len(rec[0]) == sum(3 + r for r in range(world))
+    assert np.array_equal(rec[1][:3], [0, 1, 2]) and rec[4].shape == (len(rec[0]), 2)
+    lml, theta, best = parallel.best_fit_across_processes(float(rank), np.full(3, rank))
+    assert best == world - 1 and lml == world - 1 and np.array_equal(theta, np.full(3, world - 1.))
+    # compute_y_parallel + sharded NORA on the golden ranked-pool case
+    g = load_golden("rbf_d2_n60")
+    gpr = FakeDeviceGPR(oracle_state(g))
+    Xp = golden_pool_candidates(g)
+    y, s = parallel.compute_y_parallel(gpr, Xp if rank == 0 else None, None, None,
+                                       ensure_sigma_y=True)
+    if rank == 0:
+        yo, so = orc.predict(gpr.st, Xp, return_std=True)
+        # sharded vs full-batch BLAS calls differ by round-off only
+        assert np.allclose(y, yo, rtol=1e-11, atol=1e-11) and np.allclose(s, so, rtol=1e-9, atol=1e-12)
+        assert len(y) == len(Xp)
+    nora = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=64)
+    n_points = int(g["pool_n_points"])
+    X_pool, y_pool, acq_pool = nora.multi_add(gpr, n_points=n_points, X_mc=Xp)
+    assert np.array_equal(X_pool, Xp[g["pool_idx_single_sort_acq"]])
+    np.save(os.path.join(out_dir, f"pool_{rank}.npy"), X_pool)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "pool_0.npy")
+    b = np.load(tmp_path / "pool_1.npy")
+    assert np.array_equal(a, b)      # every rank ends with the same pool (as after the bcast)
+
+
+def test_serial_fallbacks():
+    from gpry_b200 import parallel
+    assert parallel.size() == 1 and parallel.rank() == 0 and parallel.is_main_process()
+    v = np.arange(5.0)
+    assert parallel.step_split(v) is v and parallel.merge_step_split(v) is v
+    assert parallel.bcast(3) == 3 and parallel.allgather(3) == [3]
+    assert parallel.max_scalar(2.5) == 2.5
