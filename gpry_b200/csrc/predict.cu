@@ -182,7 +182,7 @@ struct VcSmem {
   double B[VC_STAGES][TILE_DOUBLES];   // K* tiles     [4 panels][128 cands][4]
   double red[2][TILE_ROWS];
   uint64_t full[VC_STAGES];
-  uint64_t empty[VC_STAGES];
+  int released[VC_STAGES];            // warps done with the stage's current contents
 };
 
 // which row-split owns row block jb (snake order: balanced triangular work)
@@ -195,8 +195,8 @@ __device__ __forceinline__ int next_owned_block(int jb, int nJ, int S, int split
   return jb;
 }
 
-// The (tile, row block, k-tile) sequence a CTA walks; used by the TMA issuer, which runs
-// VC_STAGES - 1 steps ahead of the MMA loop.
+// The (tile, row block, k-tile) sequence a CTA walks; every warp also tracks the position
+// VC_STAGES steps ahead of the MMA loop (what the slot it is consuming is refilled with).
 struct VcSeq {
   int t, jb, kt, kt_end;
   __device__ __forceinline__ void start(int n_tiles, int nJ, int S, int split, int kt_total) {
@@ -219,8 +219,45 @@ struct VcSeq {
   }
 };
 
-// grid = (min(tiles, #SM), row_splits); 256 threads = 8 MMA warps (warp tile 64 rows x 32
-// candidates, 32 DMMA accumulator fragments); lane 0 of warp 0 doubles as the TMA issuer.
+// One k-tile (16 columns = 4 panels) of a warp's accumulator tile.  The warp owns the 8-row
+// fragments f = 2 mi + rw (mi = 0..7) of the 128-row block -- interleaved between the two
+// warps that share an SM sub-partition so that both see the same triangular structure -- and
+// 32 candidates.  Fragment f meets only columns k <= row: inside the diagonal block
+// (qd = k-tile index relative to the block's first column tile, >= 0) panel p is skipped for
+// f < (4 qd + p) / 2; fragments at or beyond mi_max hold only padded rows (>= N).  All
+// predicates are warp-uniform; the DMMA pipe (one issue per 16 cycles per sub-partition)
+// leaves ample issue slots for them.
+#define VC_FRAG(mi)                                                                  \
+  {                                                                                  \
+    dmma_8x8x4(acc[mi][0][0], acc[mi][0][1], a[mi], b[0]);                           \
+    dmma_8x8x4(acc[mi][1][0], acc[mi][1][1], a[mi], b[1]);                           \
+    dmma_8x8x4(acc[mi][2][0], acc[mi][2][1], a[mi], b[2]);                           \
+    dmma_8x8x4(acc[mi][3][0], acc[mi][3][1], a[mi], b[3]);                           \
+  }
+
+// One k-tile for the fragments LO <= mi < HI of the warp (compile-time range: straight-line
+// code, no predicates, no branches).  <0, 8> is the interior tile; LO > 0 skips the fragments
+// that lie entirely above the diagonal inside a diagonal block (k-tile qd of the block only
+// meets fragments f >= 2 qd, i.e. mi >= qd for both row parities); HI < 8 drops fragments made of padded rows only.
+template <int LO, int HI>
+__device__ __forceinline__ void vc_stage(double (&acc)[8][4][2], const double* __restrict__ As,
+                                         const double* __restrict__ Bs) {
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    double a[8], b[4];
+#pragma unroll
+    for (int mi = LO; mi < HI; mi++) a[mi] = As[p * (TILE_ROWS * 4) + mi * 64];
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) b[ni] = Bs[p * (TILE_ROWS * 4) + ni * 32];
+#pragma unroll
+    for (int mi = LO; mi < HI; mi++) VC_FRAG(mi)
+  }
+}
+#undef VC_FRAG
+
+// grid = (min(tiles, #SM), row_splits); 256 threads = 8 MMA warps (warp tile: 8 interleaved
+// 8-row fragments x 32 candidates = 32 DMMA accumulator fragments); the TMA refill of a slot
+// is issued by the last warp that releases it.
 __global__ void __launch_bounds__(VC_THREADS, 1)
 var_contract_kernel(const double* __restrict__ Vt, const double* __restrict__ Ks, int n_tiles,
                     int N, int nJ, int nKT, int row_splits, double* __restrict__ ssqp,
@@ -235,35 +272,32 @@ var_contract_kernel(const double* __restrict__ Vt, const double* __restrict__ Ks
   if (tid == 0) {
     for (int s = 0; s < VC_STAGES; s++) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], VC_WARPS);
+      sm.released[s] = 0;
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  // ---- TMA issuer state (thread 0 only) ----
-  VcSeq pseq;
-  int pstage = 0;
-  uint32_t pphase = 0;
-  auto produce_one = [&]() {
-    mbar_wait(&sm.empty[pstage], pphase ^ 1);
-    mbar_expect_tx(&sm.full[pstage], 2 * TILE_BYTES);
-    tma_bulk_g2s(sm.A[pstage], Vt + (vtile_index(pseq.jb, 0) + pseq.kt) * TILE_DOUBLES,
-                 TILE_BYTES, &sm.full[pstage]);
-    tma_bulk_g2s(sm.B[pstage], Ks + ((size_t)pseq.t * nKT + pseq.kt) * TILE_DOUBLES, TILE_BYTES,
-                 &sm.full[pstage]);
-    if (++pstage == VC_STAGES) {
-      pstage = 0;
-      pphase ^= 1;
-    }
-    pseq.advance(nJ, row_splits, split, kt_total);
+  // ---- TMA issue.  Slot s is refilled by whichever warp releases it last (shared-memory
+  // counter), so no warp ever waits for another one except through the data itself. Every
+  // warp tracks the step that will next be loaded into the slot it is consuming: the
+  // consumer position + VC_STAGES. ----
+  auto issue = [&](const VcSeq& q, int slot) {
+    mbar_expect_tx(&sm.full[slot], 2 * TILE_BYTES);
+    tma_bulk_g2s(sm.A[slot], Vt + (vtile_index(q.jb, 0) + q.kt) * TILE_DOUBLES, TILE_BYTES,
+                 &sm.full[slot]);
+    tma_bulk_g2s(sm.B[slot], Ks + ((size_t)q.t * nKT + q.kt) * TILE_DOUBLES, TILE_BYTES,
+                 &sm.full[slot]);
   };
-  if (tid == 0) {
-    pseq.start(n_tiles, nJ, row_splits, split, kt_total);
-    for (int i = 0; i < VC_STAGES - 1 && pseq.valid(n_tiles); i++) produce_one();
+  VcSeq nseq;
+  nseq.start(n_tiles, nJ, row_splits, split, kt_total);
+  for (int i = 0; i < VC_STAGES; i++) {
+    if (!nseq.valid(n_tiles)) break;
+    if (tid == 0) issue(nseq, i);
+    nseq.advance(nJ, row_splits, split, kt_total);
   }
 
-  const int rw = warp >> 2;        // row half   (rows rw*64 .. +63 of the row block)
+  const int rw = warp >> 2;        // row parity: this warp owns the 8-row fragments 2*mi + rw
   const int cw = warp & 3;         // candidate quarter (cands cw*32 .. +31)
   int stage = 0;
   uint32_t phase = 0;
@@ -276,9 +310,10 @@ var_contract_kernel(const double* __restrict__ Vt, const double* __restrict__ Ks
     for (int jb = next_owned_block(0, nJ, row_splits, split); jb < nJ;
          jb = next_owned_block(jb + 1, nJ, row_splits, split)) {
       const int kt_end = min((jb + 1) * KT_PER_BLOCK, kt_total);
-      // this warp's rows need columns k <= row, i.e. k-tiles below kt_need; rows >= N are 0
-      const int row0 = jb * TILE_ROWS + rw * 64;
-      const int kt_need = (row0 >= N) ? 0 : min(kt_end, (row0 + 64) / TILE_K);
+      // fragments of this warp: f = 2 mi + rw; those with f * 8 >= (N - first row) are padding
+      const int f_max = (N - jb * TILE_ROWS + 7) / 8;          // fragments with real rows
+      const int mi_max = max(0, min(8, (f_max - rw + 1) / 2));
+      const int kt_diag0 = jb * KT_PER_BLOCK;                  // first k-tile of the diagonal block
 
       double acc[8][4][2];
 #pragma unroll
@@ -287,28 +322,42 @@ var_contract_kernel(const double* __restrict__ Vt, const double* __restrict__ Ks
         for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
       for (int kt = 0; kt < kt_end; kt++) {
-        if (tid == 0 && pseq.valid(n_tiles)) produce_one();   // refill the slot freed last step
-        __syncwarp();
         mbar_wait(&sm.full[stage], phase);
-        if (kt < kt_need) {
-          const double* As = sm.A[stage] + (rw * 64) * 4 + lane;
+        if (mi_max > 0) {
+          const double* As = sm.A[stage] + rw * 32 + lane;
           const double* Bs = sm.B[stage] + (cw * 32) * 4 + lane;
-#pragma unroll
-          for (int p = 0; p < 4; p++) {
-            double a[8], b[4];
-#pragma unroll
-            for (int mi = 0; mi < 8; mi++) a[mi] = As[p * (TILE_ROWS * 4) + mi * 32];
-#pragma unroll
-            for (int ni = 0; ni < 4; ni++) b[ni] = Bs[p * (TILE_ROWS * 4) + ni * 32];
-#pragma unroll
-            for (int mi = 0; mi < 8; mi++)
-#pragma unroll
-              for (int ni = 0; ni < 4; ni++)
-                dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+          const int qd = kt - kt_diag0;
+          if (mi_max >= 8) {
+            switch (qd < 0 ? 0 : qd) {
+              case 0: vc_stage<0, 8>(acc, As, Bs); break;
+              case 1: vc_stage<1, 8>(acc, As, Bs); break;
+              case 2: vc_stage<2, 8>(acc, As, Bs); break;
+              case 3: vc_stage<3, 8>(acc, As, Bs); break;
+              case 4: vc_stage<4, 8>(acc, As, Bs); break;
+              case 5: vc_stage<5, 8>(acc, As, Bs); break;
+              case 6: vc_stage<6, 8>(acc, As, Bs); break;
+              default: vc_stage<7, 8>(acc, As, Bs);
+            }
+          } else {   // last row block: only the fragments that hold real rows
+            switch (mi_max) {
+              case 1: vc_stage<0, 1>(acc, As, Bs); break;
+              case 2: vc_stage<0, 2>(acc, As, Bs); break;
+              case 3: vc_stage<0, 3>(acc, As, Bs); break;
+              case 4: vc_stage<0, 4>(acc, As, Bs); break;
+              case 5: vc_stage<0, 5>(acc, As, Bs); break;
+              case 6: vc_stage<0, 6>(acc, As, Bs); break;
+              default: vc_stage<0, 7>(acc, As, Bs);
+            }
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        if (lane == 0) {
+          if (atomicAdd(&sm.released[stage], 1) == VC_WARPS - 1) {   // last warp out refills
+            sm.released[stage] = 0;
+            if (nseq.valid(n_tiles)) issue(nseq, stage);
+          }
+        }
+        if (nseq.valid(n_tiles)) nseq.advance(nJ, row_splits, split, kt_total);
         if (++stage == VC_STAGES) {
           stage = 0;
           phase ^= 1;
