@@ -120,14 +120,8 @@ int gpry_state_destroy(gpry_state* st) {
     for (int b = 0; b < 2; b++) { st->tk_keys[b].release(); st->tk_idx[b].release(); }
     st->tmp.release(); st->small.release(); st->Vrm.release();
     st->pc_U.release(); st->pc_Ks.release(); st->pc_UT.release(); st->pc_G.release();
-    for (auto* ts : st->f_sets) {
-      ts->K.release(); ts->VT.release(); ts->W.release(); ts->vec.release();
-      if (ts->stream) cudaStreamDestroy(ts->stream);
-      delete ts;
-    }
-    st->f_prob.release();
-    if (st->f_pinned) cudaFreeHost(st->f_pinned);
-    if (st->f_evt) cudaEventDestroy(st->f_evt);
+    st->f_K.release(); st->f_VT.release(); st->f_W.release(); st->f_TT.release();
+    st->f_Winv.release(); st->f_misc.release(); st->f_prob.release();
     delete st;
   });
 }
@@ -153,12 +147,11 @@ int gpry_state_adopt_factorization(gpry_state* st, double c, const double* ell,
     const int N = st->f_N, d = st->f_d;
     const int Np = round_up(N, TILE_ROWS);
     std::vector<double> Xt((size_t)N * d);
-    // train.cu layouts: f_prob = [y Np][noise2 Np][X_ N*d]; set 0: VT, vec = [alpha Np]...
+    // train.cu layouts: f_prob = [y Np][noise2 Np][X_ N*d]; f_VT = V^T; f_misc = [alpha Np]...
     GPRY_CUDA(cudaMemcpy(Xt.data(), st->f_prob.p + 2 * (size_t)Np, (size_t)N * d * 8,
                          cudaMemcpyDeviceToHost));
-    upload_model(st, st->f_kind, N, d, Xt.data(), nullptr, nullptr, nullptr, st->f_sets[0]->VT.p,
-                 Np, st->f_sets[0]->vec.p /* alpha_ */, c, ell, x_min, x_width, y_mean, y_std,
-                 clip_hi);
+    upload_model(st, st->f_kind, N, d, Xt.data(), nullptr, nullptr, nullptr, st->f_VT.p, Np,
+                 st->f_misc.p /* alpha_ */, c, ell, x_min, x_width, y_mean, y_std, clip_hi);
   });
 }
 

@@ -55,12 +55,6 @@ struct EventPair {
   cudaEvent_t e0, e1;
 };
 
-// per-stream work set of the training side
-struct TrainSet {
-  DevBuf<double> K, VT, W, vec;
-  cudaStream_t stream = nullptr;
-};
-
 }  // namespace gpry
 
 struct gpry_state {
@@ -95,12 +89,9 @@ struct gpry_state {
   gpry::DevBuf<double> tmp;              // upload staging (raw V etc.)
   gpry::DevBuf<double> small;            // small outputs (gradient, top-k records)
 
-  // training-side residency (train.cu): shared problem + one work set per stream
-  std::vector<gpry::TrainSet*> f_sets;
+  // training-side residency (train.cu): shared problem + batched work buffers
+  gpry::DevBuf<double> f_K, f_VT, f_W, f_TT, f_Winv, f_misc;
   gpry::DevBuf<double> f_prob;           // [y Np][noise2 Np][X_ N*d]
-  double* f_pinned = nullptr;            // pinned host staging for per-theta results
-  size_t f_pinned_cap = 0;
-  cudaEvent_t f_evt = nullptr;
   int f_N = 0, f_d = 0, f_kind = -1;
   bool f_valid = false;
 

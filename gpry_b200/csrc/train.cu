@@ -1,22 +1,29 @@
 // Training-side hot path: kernel matrix, blocked FP64 Cholesky, L^-1, alpha, log marginal
-// likelihood and its gradient.
+// likelihood and its gradient -- for a BATCH of hyper-parameter vectors at once.
 //
 // Reference arithmetic: gpr.py:1015-1017, 1453-1465 (_update_model / _kernel_inverse);
 // sklearn:_gpr.py:584-651 (LML + gradient); kernel values and theta-gradients
 // sklearn:kernels.py:1561-1584 (RBF), 1716-1771 (Matern), 964-969 (Product), 1283-1292
 // (Constant).
 //
-// Everything works on matrices padded to Np = round_up(N, 128) with an identity block in the
-// padding (unit diagonal, zero coupling), so every tile is full and the padded rows leave
-// L, L^-1, alpha and log det untouched.
+// Matrices are padded to Np = round_up(N, 128) with an identity block in the padding (unit
+// diagonal, zero coupling): every tile is full and the padded rows leave L, L^-1, alpha and
+// log det untouched.  All kernels take the batch index from the grid (one theta per z / x).
 //
-//   kmat_kernel        K = c g(r) + diag(noise2)                       (lower tiles)
-//   potf2_inv_kernel   128 x 128 diagonal block: L_jj and W_jj = L_jj^-1 (one CTA: 32 x 32
-//                      sub-blocks factored in registers by one warp, 32^3 products on DMMA)
+//   kmat_kernel        K = c g(r) + diag(noise2)                            (lower tiles)
+//   potf2_inv_kernel   128 x 128 diagonal block: L_jj, W_jj = L_jj^-1 (one CTA per theta:
+//                      32 x 32 sub-blocks factored in registers by one warp, all 32^3 block
+//                      products on DMMA); also writes the diagonal block of V^T
 //   gemm_nt_kernel     C (+)= alpha A B^T on FP64 tensor cores (DMMA.8x8x4), cp.async
-//                      4-stage pipeline; used for the panel solve (x W_jj^T), the SYRK
-//                      trailing update, the right-looking sweep that builds V^T = L^-T and
-//                      K^-1 = V^T V (block-triangular k ranges skip the structural zeros)
+//                      4-stage pipeline, up to two row segments sharing the B operand.
+//                      LEFT-LOOKING blocked algorithm: per block column j
+//                        (1) A[j:, j] -= L[j:, :j] L[j, :j]^T      fused with
+//                            TT      =  V^T[:j, :j..] L[j, :j]^T   (same B operand, long K)
+//                        (2) potf2_inv on the diagonal block
+//                        (3) L[j+1:, j] = A[j+1:, j] W_jj^T        fused with
+//                            V^T[:j, j] = -TT W_jj^T               (same B operand W_jj)
+//                      then K^-1 = V^T V (block-triangular k range).  Every output tile is
+//                      written once; no trailing-matrix read-modify-write sweeps.
 //   lml_grad_kernel    fused trace contraction 1/2 sum_ij (a_i a_j - K^-1_ij) dK_ij/dtheta:
 //                      kernel values and per-dimension distances are recomputed per pair,
 //                      dK/dtheta (N x N x (1+d)) is never materialised
@@ -44,13 +51,17 @@ __device__ __forceinline__ double stationary_value(double r2) {
   return (1.0 + K + K * K / 3.0) * exp(-K);
 }
 
-// T = X_ / ell (row major N x d).  32 x 32 tile per CTA (lower tiles incl. diagonal).
+
+// T = X_ / ell (row major N x d per theta).  32 x 32 tile per CTA (lower tiles incl. diagonal).
 template <int KIND>
 __global__ void __launch_bounds__(256)
-kmat_kernel(const double* __restrict__ T, int N, int d, int Np, double c,
-            const double* __restrict__ noise2, double* __restrict__ K) {
-  const int bi = blockIdx.y, bj = blockIdx.x;
+kmat_kernel(const double* __restrict__ Tall, int N, int d, int Np, const double* __restrict__ cs,
+            const double* __restrict__ noise2, double* __restrict__ Kall) {
+  const int bi = blockIdx.y, bj = blockIdx.x, th = blockIdx.z;
   if (bj > bi) return;
+  const double* T = Tall + (size_t)th * N * d;
+  double* K = Kall + (size_t)th * Np * Np;
+  const double c = cs[th];
   extern __shared__ double sh[];
   double* Ti = sh;                    // [32][d+1]
   double* Tj = sh + 32 * (d + 1);     // [32][d+1]
@@ -83,9 +94,9 @@ kmat_kernel(const double* __restrict__ T, int N, int d, int Np, double c,
 }
 
 // ---------------------------------------------------------------------------------------
-// diagonal block: 128 x 128 Cholesky + triangular inverse in ONE CTA (8 warps).
+// diagonal block: 128 x 128 Cholesky + triangular inverse in ONE CTA (8 warps) per theta.
 //   A: the diagonal block (leading dimension ld), overwritten by L_jj (upper triangle zeroed)
-//   W: dense 128 x 128 = L_jj^-1 (upper zeroed)
+//   W: dense 128 x 128 = L_jj^-1 (upper zeroed);  VTd: diagonal block of V^T = W^T
 //   info: first failing global pivot index + 1 (0 = ok)
 // The block is split in 4 x 4 sub-blocks of 32 x 32 held in shared memory ([32][36] padded,
 // conflict-free for the DMMA fragment loads).  A 32 x 32 diagonal sub-block is factored and
@@ -187,8 +198,13 @@ __device__ __forceinline__ void factor_inv_32(double* __restrict__ D, double* __
 }
 
 __global__ void __launch_bounds__(256)
-potf2_inv_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int row_offset,
-                 int* __restrict__ info) {
+potf2_inv_kernel(double* __restrict__ Aall, size_t sA, int ld, double* __restrict__ Wall, size_t sW,
+                 double* __restrict__ VTall, size_t sVT, int row_offset,
+                 int* __restrict__ info_all) {
+  double* A = Aall + blockIdx.x * sA;
+  double* W = Wall + blockIdx.x * sW;
+  double* VTd = VTall + blockIdx.x * sVT;
+  int* info = info_all + blockIdx.x;
   extern __shared__ double sh[];
   double* Lb = sh;                       // 10 lower sub-blocks of the block / of L
   double* Wb = sh + 10 * SB_DOUBLES;     // 10 lower sub-blocks of the inverse
@@ -256,27 +272,38 @@ potf2_inv_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int row
     }
     A[(size_t)r * ld + cidx] = lv;
     W[e] = wv;
+    // V^T diagonal block: VTd[a][b] = W[b][a]
+    double wt = 0.0;
+    if (bi <= bj) wt = Wb[sbidx(bj, bi) * SB_DOUBLES + (cidx & 31) * SBLD + (r & 31)];
+    VTd[(size_t)r * ld + cidx] = wt;
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// FP64 tensor-core GEMM, C (+)= alpha * A * B^T   (A: M x K, B: N x K, both k-contiguous)
+// FP64 tensor-core GEMM, C (+)= alpha * A * B^T   (A: M x K, B: N x K, both k-contiguous),
+// batched over blockIdx.z, with up to two row segments that share the B operand.
 // ---------------------------------------------------------------------------------------
 constexpr int G_STAGES = 4;
 constexpr int G_THREADS = 256;
-enum { G_FILTER_ALL = 0, G_FILTER_LOWER = 1 };
-enum { G_KLO_ZERO = 0, G_KLO_ROW = 1 };
 
-struct GemmArgs {
+struct GemmSeg {
   const double* A;
-  const double* B;
   double* C;
-  int lda, ldb, ldc;
-  int M, N, K;          // multiples of 128, 128, 16
+  int lda, ldc;
+  int m_tiles;          // 128-row tiles in this segment
   double alpha;
   int accumulate;       // 0: C = alpha A B^T ; 1: C += alpha A B^T
-  int filter;           // G_FILTER_LOWER: only tiles with tile_row >= tile_col
-  int klo_mode;         // G_KLO_ROW: k starts at the tile's first row (A upper triangular)
+  int klo_row;          // 1: k starts at the tile's first row (A upper triangular)
+  size_t sA, sC;        // batch strides (doubles)
+};
+struct GemmArgs {
+  GemmSeg seg[2];
+  const double* B;
+  int ldb;
+  size_t sB;
+  int n_tiles;          // 128-column tiles of C (rows of B)
+  int K;                // multiple of 16
+  int lower_only;       // only tiles with tile_row >= tile_col (segment 0)
 };
 
 struct GemmSmem {
@@ -294,26 +321,33 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
-  const int mt = blockIdx.y, nt = blockIdx.x;
-  if (g.filter == G_FILTER_LOWER && mt < nt) return;
+  int mt = blockIdx.y;
+  const int nt = blockIdx.x;
+  const int si = (mt >= g.seg[0].m_tiles) ? 1 : 0;
+  if (si) mt -= g.seg[0].m_tiles;
+  const GemmSeg& sg = g.seg[si];
+  if (g.lower_only && mt < nt) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = mt * TILE_ROWS, n0 = nt * TILE_ROWS;
-  const int k_lo = (g.klo_mode == G_KLO_ROW) ? m0 : 0;
+  const int k_lo = sg.klo_row ? m0 : 0;
   const int nk = (g.K - k_lo) / TILE_K;
+  const size_t bz = blockIdx.z;
 
-  const double* Ag = g.A + (size_t)m0 * g.lda + k_lo;
-  const double* Bg = g.B + (size_t)n0 * g.ldb + k_lo;
+  const double* Ag = sg.A + bz * sg.sA + (size_t)m0 * sg.lda + k_lo;
+  const double* Bg = g.B + bz * g.sB + (size_t)n0 * g.ldb + k_lo;
+  const int lda = sg.lda, ldb = g.ldb;
   auto load_stage = [&](int s, int kt) {
     const int k0 = kt * TILE_K;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       int q = tid + G_THREADS * i;        // 0..1023: 16-byte chunk id
       int row = q >> 3, kc = (q & 7) * 2;
-      cp_async16(&sm.A[s][tile_elem(row, kc)], Ag + (size_t)row * g.lda + k0 + kc);
-      cp_async16(&sm.B[s][tile_elem(row, kc)], Bg + (size_t)row * g.ldb + k0 + kc);
+      cp_async16(&sm.A[s][tile_elem(row, kc)], Ag + (size_t)row * lda + k0 + kc);
+      cp_async16(&sm.B[s][tile_elem(row, kc)], Bg + (size_t)row * ldb + k0 + kc);
     }
   };
   for (int s = 0; s < G_STAGES - 1; s++) {
@@ -352,17 +386,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
     }
   }
   cp_async_wait<0>();
+  __syncthreads();   // in-place segments: every warp's operand reads are done before C is written
   // epilogue
   const int g8 = lane >> 2, t4 = lane & 3;
+  double* Cg = sg.C + bz * sg.sC;
+  const double alpha = sg.alpha;
+  const int ldc = sg.ldc;
 #pragma unroll
   for (int mi = 0; mi < 8; mi++)
 #pragma unroll
     for (int ni = 0; ni < 4; ni++) {
       int row = m0 + rw * 64 + mi * 8 + g8;
       int col = n0 + cw * 32 + ni * 8 + 2 * t4;
-      double2* cp = reinterpret_cast<double2*>(g.C + (size_t)row * g.ldc + col);
-      double2 v = make_double2(g.alpha * acc[mi][ni][0], g.alpha * acc[mi][ni][1]);
-      if (g.accumulate) {
+      double2* cp = reinterpret_cast<double2*>(Cg + (size_t)row * ldc + col);
+      double2 v = make_double2(alpha * acc[mi][ni][0], alpha * acc[mi][ni][1]);
+      if (sg.accumulate) {
         double2 o = *cp;
         v.x += o.x;
         v.y += o.y;
@@ -371,43 +409,45 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
     }
 }
 
-static void launch_gemm(const GemmArgs& g, cudaStream_t s) {
-  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return;
-  dim3 grid(g.N / TILE_ROWS, g.M / TILE_ROWS);
+static void launch_gemm(const GemmArgs& g, int batch, cudaStream_t s) {
+  const int mt = g.seg[0].m_tiles + g.seg[1].m_tiles;
+  if (mt <= 0 || g.n_tiles <= 0 || g.K <= 0 || batch <= 0) return;
+  dim3 grid(g.n_tiles, mt, batch);
   gemm_nt_kernel<<<grid, G_THREADS, sizeof(GemmSmem), s>>>(g);
   GPRY_CUDA(cudaGetLastError());
+}
+static void gemm_prepare() {
+  GPRY_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(GemmSmem)));
 }
 
 void gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N,
              int K, double alpha, int accumulate, int lower_only, int klo_row, cudaStream_t s) {
   GemmArgs g{};
-  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
-  g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.accumulate = accumulate;
-  g.filter = lower_only ? G_FILTER_LOWER : G_FILTER_ALL;
-  g.klo_mode = klo_row ? G_KLO_ROW : G_KLO_ZERO;
-  GPRY_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(GemmSmem)));
-  launch_gemm(g, s);
+  g.seg[0] = GemmSeg{A, C, lda, ldc, M / TILE_ROWS, alpha, accumulate, klo_row, 0, 0};
+  g.seg[1].m_tiles = 0;
+  g.B = B; g.ldb = ldb; g.sB = 0;
+  g.n_tiles = N / TILE_ROWS; g.K = K; g.lower_only = lower_only;
+  gemm_prepare();
+  launch_gemm(g, 1, s);
 }
 
 // ---------------------------------------------------------------------------------------
-// small helpers
+// small helpers (batch index = blockIdx.y unless noted)
 // ---------------------------------------------------------------------------------------
-__global__ void set_identity_kernel(double* __restrict__ A, int Np) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (int64_t)Np * Np) return;
-  int r = (int)(e / Np), cidx = (int)(e % Np);
-  A[e] = r == cidx ? 1.0 : 0.0;
-}
+// Tall[th][e] = X[e] / ell[th][e % d]
 __global__ void scale_rows_kernel(const double* __restrict__ X, int N, int d,
-                                  const double* __restrict__ ell, double* __restrict__ T) {
+                                  const double* __restrict__ ells, double* __restrict__ Tall) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < N * d) T[e] = X[e] / ell[e % d];
+  const int th = blockIdx.y;
+  if (e < N * d) Tall[(size_t)th * N * d + e] = X[e] / ells[(size_t)th * MAX_DIM + e % d];
 }
 // t = V y = VT^T y : CTA per 32 columns of VT, 8 row groups, rows j <= i; fixed-order sums
 __global__ void __launch_bounds__(256)
-gemv_vt_t_kernel(const double* __restrict__ VT, int Np, int N, const double* __restrict__ y,
-                 double* __restrict__ t) {
+gemv_vt_t_kernel(const double* __restrict__ VTall, int Np, int N, const double* __restrict__ y,
+                 double* __restrict__ tall) {
+  const double* VT = VTall + (size_t)blockIdx.y * Np * Np;
+  double* t = tall + (size_t)blockIdx.y * Np;
   __shared__ double red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + cx;
@@ -426,8 +466,11 @@ gemv_vt_t_kernel(const double* __restrict__ VT, int Np, int N, const double* __r
   }
 }
 // alpha = V^T t = VT t : warp per row j, columns i >= j
-__global__ void gemv_vt_kernel(const double* __restrict__ VT, int Np, int N,
-                               const double* __restrict__ t, double* __restrict__ alpha) {
+__global__ void gemv_vt_kernel(const double* __restrict__ VTall, int Np, int N,
+                               const double* __restrict__ tall, double* __restrict__ alpha_all) {
+  const double* VT = VTall + (size_t)blockIdx.y * Np * Np;
+  const double* t = tall + (size_t)blockIdx.y * Np;
+  double* alpha = alpha_all + (size_t)blockIdx.y * Np;
   int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (j >= Np) return;
@@ -437,10 +480,14 @@ __global__ void gemv_vt_kernel(const double* __restrict__ VT, int Np, int N,
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) alpha[j] = s;
 }
-// out[0] = sum_i log L_ii, out[1] = y . alpha      (single block, fixed order)
-__global__ void lml_scalars_kernel(const double* __restrict__ L, int Np, int N,
-                                   const double* __restrict__ y, const double* __restrict__ alpha,
-                                   double* __restrict__ out) {
+// out[th][0] = sum_i log L_ii, out[th][1] = y . alpha      (one block per theta, fixed order)
+__global__ void lml_scalars_kernel(const double* __restrict__ Lall, int Np, int N,
+                                   const double* __restrict__ y,
+                                   const double* __restrict__ alpha_all,
+                                   double* __restrict__ out_all) {
+  const double* L = Lall + (size_t)blockIdx.x * Np * Np;
+  const double* alpha = alpha_all + (size_t)blockIdx.x * Np;
+  double* out = out_all + (size_t)blockIdx.x * 2;
   __shared__ double r0[256], r1[256];
   double a = 0.0, b = 0.0;
   for (int i = threadIdx.x; i < N; i += 256) {
@@ -472,36 +519,34 @@ __global__ void extract_kernel(const double* __restrict__ src, int Np, int N, in
   if (cidx <= r) v = transpose ? src[(size_t)cidx * Np + r] : src[(size_t)r * Np + cidx];
   dst[e] = v;
 }
-__global__ void transpose_block_kernel(const double* __restrict__ W, double* __restrict__ dst,
-                                       int ld) {
-  // dst[a][b] = W[b][a], 128 x 128
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 128 * 128) return;
-  int a = e >> 7, b = e & 127;
-  dst[(size_t)a * ld + b] = W[b * 128 + a];
-}
 
 // ---------------------------------------------------------------------------------------
 // fused LML-gradient trace contraction
 //   grad_p = 1/2 sum_ij (alpha_i alpha_j - Kinv_ij) dK_ij / dtheta_p   (sklearn:_gpr.py:647)
 // 32 x 32 tile of pairs per CTA over the lower triangle; off-diagonal tiles count twice.
-// partial[(tile)][p] written per CTA, reduced in fixed order by reduce_partials_kernel.
+// partial[th][tile][p] written per CTA, reduced in fixed order by reduce_partials_kernel.
 // ---------------------------------------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(256)
-lml_grad_kernel(const double* __restrict__ X, const double* __restrict__ T, int N, int d, int Np,
-                double c, const double* __restrict__ ell, const double* __restrict__ alpha,
-                const double* __restrict__ Kinv, double* __restrict__ partial, int P) {
-  const int bi = blockIdx.y, bj = blockIdx.x;
+lml_grad_kernel(const double* __restrict__ X, const double* __restrict__ Tall, int N, int d,
+                int Np, const double* __restrict__ cs, const double* __restrict__ ells,
+                const double* __restrict__ alpha_all, const double* __restrict__ Kinv_all,
+                double* __restrict__ partial_all, int P) {
+  const int bi = blockIdx.y, bj = blockIdx.x, th = blockIdx.z;
   const int nb = gridDim.x;
-  double* out = partial + ((size_t)bi * nb + bj) * P;
+  const double* T = Tall + (size_t)th * N * d;
+  const double* ell = ells + (size_t)th * MAX_DIM;
+  const double* alpha = alpha_all + (size_t)th * Np;
+  const double* Kinv = Kinv_all + (size_t)th * Np * Np;
+  const double c = cs[th];
+  double* out = partial_all + (((size_t)th * nb + bi) * nb + bj) * P;
   extern __shared__ double sh[];
   double* Xi = sh;                      // [32][d+1]
   double* Xj = Xi + 32 * (d + 1);       // [32][d+1]
   double* Ti = Xj + 32 * (d + 1);       // [32][d+1]  X / ell
   double* Tj = Ti + 32 * (d + 1);       // [32][d+1]
-  double* inv_l2 = Tj + 32 * (d + 1);   // [d]  ell^2 (divided by, as the reference does)
-  double* red = inv_l2 + d;             // [8 warps][P]
+  double* l2 = Tj + 32 * (d + 1);       // [d]  ell^2 (divided by, as the reference does)
+  double* red = l2 + d;                 // [8 warps][P]
   const int tid = threadIdx.x;
   if (bj > bi) {
     for (int p = tid; p < P; p += 256) out[p] = 0.0;
@@ -515,7 +560,7 @@ lml_grad_kernel(const double* __restrict__ X, const double* __restrict__ T, int 
     Ti[r * (d + 1) + k] = gi < N ? T[(size_t)gi * d + k] : 0.0;
     Tj[r * (d + 1) + k] = gj < N ? T[(size_t)gj * d + k] : 0.0;
   }
-  for (int k = tid; k < d; k += 256) inv_l2[k] = ell[k] * ell[k];   // length_scale**2
+  for (int k = tid; k < d; k += 256) l2[k] = ell[k] * ell[k];   // length_scale**2
   __syncthreads();
   const int tx = tid & 31, ty = tid >> 5, lane = tx, warp = ty;
   // each thread: column tx, rows ty + 8 q.  Pass 1 computes w * (kernel factor) per pair and
@@ -537,7 +582,7 @@ lml_grad_kernel(const double* __restrict__ X, const double* __restrict__ T, int 
         double sumD = 0.0, r2 = 0.0;
         for (int k = 0; k < d; k++) {
           double df = Xi[rr * (d + 1) + k] - Xj[tx * (d + 1) + k];
-          double D = df * df / inv_l2[k];         // (xi - xj)**2 / length_scale**2
+          double D = df * df / l2[k];             // (xi - xj)**2 / length_scale**2
           sumD += D;
           double a = Ti[rr * (d + 1) + k] - Tj[tx * (d + 1) + k];
           r2 = fma(a, a, r2);                     // pdist(X / l): the value entering K itself
@@ -559,7 +604,6 @@ lml_grad_kernel(const double* __restrict__ X, const double* __restrict__ T, int 
       }
     }
   }
-  // reduce g0 over the block
   auto block_sum_to = [&](double v, int p) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) red[warp * P + p] = v;
@@ -571,7 +615,7 @@ lml_grad_kernel(const double* __restrict__ X, const double* __restrict__ T, int 
     for (int q = 0; q < 4; q++) {
       const int rr = ty + 8 * q;
       double df = Xi[rr * (d + 1) + k] - Xj[tx * (d + 1) + k];
-      s = fma(wk[q], df * df / inv_l2[k], s);
+      s = fma(wk[q], df * df / l2[k], s);
     }
     block_sum_to(s, 1 + k);
   }
@@ -583,11 +627,12 @@ lml_grad_kernel(const double* __restrict__ X, const double* __restrict__ T, int 
   }
 }
 
-__global__ void reduce_partials_kernel(const double* __restrict__ partial, int n, int P,
-                                       double* __restrict__ out) {
-  // one block per p; fixed-order tree
+// grid (P, B): out[th][p] = sum over tiles, fixed-order tree
+__global__ void reduce_partials_kernel(const double* __restrict__ partial_all, int n, int P,
+                                       double* __restrict__ out_all) {
   __shared__ double r[256];
-  const int p = blockIdx.x;
+  const int p = blockIdx.x, th = blockIdx.y;
+  const double* partial = partial_all + (size_t)th * n * P;
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) s += partial[(size_t)i * P + p];
   r[threadIdx.x] = s;
@@ -596,71 +641,65 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
     if (threadIdx.x < o) r[threadIdx.x] += r[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[p] = r[0];
+  if (threadIdx.x == 0) out_all[(size_t)th * (MAX_DIM + 8) + p] = r[0];
 }
 
 // ---------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------
 struct TrainBuffers {
-  int N, d, Np, nb;
-  double *K, *VT, *W;         // Np x Np each (W: K^-1, only for the gradient)
-  double *Winv;               // nb x 128 x 128
-  double *X, *T, *noise2, *y, *ell, *alpha, *t, *scal, *partial, *grad;
+  int N, d, Np, nb, B;        // B = thetas per sub-batch
+  double *K, *VT, *W;         // [B][Np][Np] each (W: K^-1, only for the gradient)
+  double *TT;                 // [B][Np][128]
+  double *Winv;               // [B][nb][128][128]
+  double *X, *noise2, *y;     // shared problem
+  double *T, *ells, *cs, *alpha, *t, *scal, *partial, *grad;
   int* info;
-  cudaStream_t stream;
 };
 
-constexpr int MAX_TRAIN_STREAMS = 4;
-
-// shared problem: st->f_prob = [y Np][noise2 Np][X_ N*d][ell of each theta: B x MAX_DIM]
-// per-set vec:    [alpha Np][t Np][T N*d][ell MAX_DIM][scal 8][grad MAX_DIM+8][info 2]
-//                 [Winv nb*128*128][partial nb32*nb32*P]
-static TrainBuffers carve(gpry_state* st, int set, int N, int d, bool need_grad, int B) {
+// f_prob : [y Np][noise2 Np][X_ N*d]
+// f_misc : [alpha B*Np][t B*Np][T B*nXd][ells B*MAX_DIM][cs B][scal B*2][grad B*(MAX_DIM+8)]
+//          [info B ints][partial B*nb32^2*P]
+static TrainBuffers carve(gpry_state* st, int N, int d, bool need_grad, int B) {
   TrainBuffers b;
-  b.N = N;
-  b.d = d;
+  b.N = N; b.d = d; b.B = B;
   b.Np = round_up(N, NB);
   b.nb = b.Np / NB;
-  const size_t Np = b.Np;
-  while ((int)st->f_sets.size() <= set) {
-    TrainSet* ts = new TrainSet();
-    GPRY_CUDA(cudaStreamCreateWithFlags(&ts->stream, cudaStreamNonBlocking));
-    st->f_sets.push_back(ts);
-  }
-  TrainSet* ts = st->f_sets[set];
-  ts->K.reserve(Np * Np);
-  ts->VT.reserve(Np * Np);
-  if (need_grad) ts->W.reserve(Np * Np);
-  const int nb32 = (N + 31) / 32;
-  const int P = d + 1;
+  const size_t Np = b.Np, NN = Np * Np;
   auto al = [](size_t x) { return (x + 31) / 32 * 32; };   // 256-byte aligned segments
+  st->f_K.reserve(NN * B);
+  st->f_VT.reserve(NN * B);
+  if (need_grad) st->f_W.reserve(NN * B);
+  st->f_TT.reserve(Np * NB * B);
+  st->f_Winv.reserve((size_t)b.nb * NB * NB * B);
   const size_t nXd = al((size_t)N * d);
-  size_t n = 2 * Np + nXd + al(MAX_DIM) + 32 + al(MAX_DIM + 8) + 32 + (size_t)b.nb * NB * NB +
-             (need_grad ? (size_t)nb32 * nb32 * P : 0) + 64;
-  ts->vec.reserve(n);
-  st->f_prob.reserve(2 * Np + nXd + (size_t)B * MAX_DIM);
+  st->f_prob.reserve(2 * Np + nXd);
+  const int nb32 = (N + 31) / 32, P = d + 1;
+  size_t n = 2 * Np * B + nXd * B + al((size_t)MAX_DIM * B) + al(B) + al(2 * (size_t)B) +
+             al((size_t)(MAX_DIM + 8) * B) + al(B) + (need_grad ? (size_t)nb32 * nb32 * P * B : 0) + 64;
+  st->f_misc.reserve(n);
   b.y = st->f_prob.p;
   b.noise2 = b.y + Np;
   b.X = b.noise2 + Np;
-  double* p = ts->vec.p;
-  b.alpha = p; p += Np;
-  b.t = p; p += Np;
-  b.T = p; p += nXd;
-  b.ell = p; p += al(MAX_DIM);
-  b.scal = p; p += 32;
-  b.grad = p; p += al(MAX_DIM + 8);
-  b.info = reinterpret_cast<int*>(p); p += 32;
-  b.Winv = p; p += (size_t)b.nb * NB * NB;
+  double* p = st->f_misc.p;
+  b.alpha = p; p += Np * B;
+  b.t = p; p += Np * B;
+  b.T = p; p += nXd * B;
+  b.ells = p; p += al((size_t)MAX_DIM * B);
+  b.cs = p; p += al(B);
+  b.scal = p; p += al(2 * (size_t)B);
+  b.grad = p; p += al((size_t)(MAX_DIM + 8) * B);
+  b.info = reinterpret_cast<int*>(p); p += al(B);
   b.partial = p;
-  b.K = ts->K.p;
-  b.VT = ts->VT.p;
-  b.W = need_grad ? ts->W.p : nullptr;
-  b.stream = ts->stream;
+  b.K = st->f_K.p;
+  b.VT = st->f_VT.p;
+  b.W = need_grad ? st->f_W.p : nullptr;
+  b.TT = st->f_TT.p;
+  b.Winv = st->f_Winv.p;
   return b;
 }
 
-static void upload_problem(gpry_state* st, TrainBuffers& b, const double* X, const double* noise2,
+static void upload_problem(const TrainBuffers& b, const double* X, const double* noise2,
                            const double* y, cudaStream_t s) {
   const size_t Np = b.Np;
   GPRY_CUDA(cudaMemsetAsync(b.y, 0, 2 * Np * 8, s));
@@ -669,135 +708,118 @@ static void upload_problem(gpry_state* st, TrainBuffers& b, const double* X, con
   GPRY_CUDA(cudaMemcpyAsync(b.y, y, (size_t)b.N * 8, cudaMemcpyHostToDevice, s));
 }
 
-// exp(theta[1:]) of all B evaluations -> device (one pageable copy, before any kernel runs)
-static double* upload_ells(gpry_state* st, const TrainBuffers& b, const double* thetas, int B,
-                           cudaStream_t s) {
-  const int P = b.d + 1;
-  std::vector<double> ells((size_t)B * MAX_DIM, 1.0);
-  for (int i = 0; i < B; i++)
-    for (int k = 0; k < b.d; k++) ells[(size_t)i * MAX_DIM + k] = exp(thetas[(size_t)i * P + 1 + k]);
-  double* dst = b.X + ((size_t)b.N * b.d + 31) / 32 * 32;
-  GPRY_CUDA(cudaMemcpyAsync(dst, ells.data(), ells.size() * 8, cudaMemcpyHostToDevice, s));
-  return dst;
-}
-
 template <int KIND>
-static void launch_kmat(const TrainBuffers& b, double c, cudaStream_t s) {
+static void launch_kmat(const TrainBuffers& b, int nth, cudaStream_t s) {
   const int nb32 = b.Np / 32;
   size_t smem = 2 * 32 * (size_t)(b.d + 1) * 8;
-  kmat_kernel<KIND><<<dim3(nb32, nb32), 256, smem, s>>>(b.T, b.N, b.d, b.Np, c, b.noise2, b.K);
+  const size_t nXd = ((size_t)b.N * b.d + 31) / 32 * 32;
+  (void)nXd;
+  kmat_kernel<KIND><<<dim3(nb32, nb32, nth), 256, smem, s>>>(b.T, b.N, b.d, b.Np, b.cs, b.noise2,
+                                                            b.K);
   GPRY_CUDA(cudaGetLastError());
 }
 
 template <int KIND>
-static void launch_grad(const TrainBuffers& b, double c, int nb32, cudaStream_t s) {
+static void launch_grad(const TrainBuffers& b, int nth, int nb32, cudaStream_t s) {
   const int P = b.d + 1;
   size_t smem = (4 * 32 * (size_t)(b.d + 1) + b.d + 8 * (size_t)P) * 8;
-  lml_grad_kernel<KIND><<<dim3(nb32, nb32), 256, smem, s>>>(b.X, b.T, b.N, b.d, b.Np, c, b.ell, b.alpha,
-                                                            b.W, b.partial, P);
+  if (smem > 48 * 1024)
+    GPRY_CUDA(cudaFuncSetAttribute(lml_grad_kernel<KIND>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lml_grad_kernel<KIND><<<dim3(nb32, nb32, nth), 256, smem, s>>>(
+      b.X, b.T, b.N, b.d, b.Np, b.cs, b.ells, b.alpha, b.W, b.partial, P);
   GPRY_CUDA(cudaGetLastError());
 }
 
-// K(theta) -> L (in K), VT = L^-T, alpha, scal = {sum log diag L, y.alpha}; optionally
-// W = K^-1 and grad (device).  Returns nothing; info stays on the device.
-// b.ell must already point at the device copy of exp(theta[1:]) for this evaluation.
-static void factorize_on_device(gpry_state* st, TrainBuffers& b, int kind, const double* theta,
-                                bool need_grad, cudaStream_t s) {
-  const int N = b.N, d = b.d, Np = b.Np, nb = b.nb;
-  const double c = exp(theta[0]);
-  GPRY_CUDA(cudaMemsetAsync(b.info, 0, 8, s));
-  scale_rows_kernel<<<(N * d + 255) / 256, 256, 0, s>>>(b.X, N, d, b.ell, b.T);
+// For nth thetas (host array, stride P): K -> L (in K), VT = L^-T, alpha, scal = {sum log diag
+// L, y.alpha}; optionally W = K^-1 and grad.  Everything stays on the device.
+static void factorize_batch(gpry_state* st, TrainBuffers& b, int kind, const double* thetas,
+                            int nth, bool need_grad, cudaStream_t s) {
+  const int N = b.N, d = b.d, Np = b.Np, nb = b.nb, P = d + 1;
+  const size_t NN = (size_t)Np * Np;
+  // exp(theta) -> device (pageable copy: staged before this call returns)
+  {
+    std::vector<double> h((size_t)MAX_DIM * nth + nth, 1.0);
+    for (int i = 0; i < nth; i++) {
+      for (int k = 0; k < d; k++) h[(size_t)i * MAX_DIM + k] = exp(thetas[(size_t)i * P + 1 + k]);
+      h[(size_t)MAX_DIM * nth + i] = exp(thetas[(size_t)i * P]);
+    }
+    GPRY_CUDA(cudaMemcpyAsync(b.ells, h.data(), (size_t)MAX_DIM * nth * 8, cudaMemcpyHostToDevice, s));
+    GPRY_CUDA(cudaMemcpyAsync(b.cs, h.data() + (size_t)MAX_DIM * nth, (size_t)nth * 8,
+                              cudaMemcpyHostToDevice, s));
+  }
+  GPRY_CUDA(cudaMemsetAsync(b.info, 0, (size_t)nth * sizeof(int), s));
+  scale_rows_kernel<<<dim3((N * d + 255) / 256, nth), 256, 0, s>>>(b.X, N, d, b.ells, b.T);
   GPRY_CUDA(cudaGetLastError());
   switch (kind) {
-    case GPRY_KERNEL_RBF: launch_kmat<GPRY_KERNEL_RBF>(b, c, s); break;
-    case GPRY_KERNEL_MATERN15: launch_kmat<GPRY_KERNEL_MATERN15>(b, c, s); break;
-    default: launch_kmat<GPRY_KERNEL_MATERN25>(b, c, s);
+    case GPRY_KERNEL_RBF: launch_kmat<GPRY_KERNEL_RBF>(b, nth, s); break;
+    case GPRY_KERNEL_MATERN15: launch_kmat<GPRY_KERNEL_MATERN15>(b, nth, s); break;
+    default: launch_kmat<GPRY_KERNEL_MATERN25>(b, nth, s);
   }
-  {
-    int64_t tot = (int64_t)Np * Np;
-    set_identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(b.VT, Np);
-    GPRY_CUDA(cudaGetLastError());
-  }
-  GPRY_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(GemmSmem)));
+  gemm_prepare();
   const size_t potf2_smem = 20 * (size_t)SB_DOUBLES * 8;
   GPRY_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)potf2_smem));
+  const size_t sWinv = (size_t)nb * NB * NB, sTT = (size_t)Np * NB;
   for (int j = 0; j < nb; j++) {
-    double* Ajj = b.K + (size_t)j * NB * (Np + 1);
-    double* Wj = b.Winv + (size_t)j * NB * NB;
-    potf2_inv_kernel<<<1, 256, potf2_smem, s>>>(Ajj, Np, Wj, j * NB, b.info);
-    GPRY_CUDA(cudaGetLastError());
-    const int rem = Np - (j + 1) * NB;
-    if (rem > 0) {
-      // panel: L[j+1:, j] = A[j+1:, j] W_jj^T        (in place)
+    const size_t jB = (size_t)j * NB;
+    if (j > 0) {
+      // (1) block column j of A minus the contribution of the finished columns, and the
+      //     V^T row-sweep product, sharing the B operand L[j, :j]
       GemmArgs g{};
-      g.A = b.K + (size_t)(j + 1) * NB * Np + (size_t)j * NB;
-      g.lda = Np;
-      g.B = Wj;
-      g.ldb = NB;
-      g.C = const_cast<double*>(g.A);
-      g.ldc = Np;
-      g.M = rem; g.N = NB; g.K = NB;
-      g.alpha = 1.0; g.accumulate = 0; g.filter = G_FILTER_ALL; g.klo_mode = G_KLO_ZERO;
-      launch_gemm(g, s);
-      // trailing update: A[j+1:, j+1:] -= P P^T      (lower tiles)
-      GemmArgs u{};
-      u.A = g.A; u.lda = Np; u.B = g.A; u.ldb = Np;
-      u.C = b.K + (size_t)(j + 1) * NB * (Np + 1);
-      u.ldc = Np;
-      u.M = rem; u.N = rem; u.K = NB;
-      u.alpha = -1.0; u.accumulate = 1; u.filter = G_FILTER_LOWER; u.klo_mode = G_KLO_ZERO;
-      launch_gemm(u, s);
+      g.seg[0] = GemmSeg{b.K + jB * Np, b.K + jB * Np + jB, Np, Np, nb - j, -1.0, 1, 0, NN, NN};
+      g.seg[1] = GemmSeg{b.VT, b.TT, Np, NB, j, 1.0, 0, 1, NN, sTT};
+      g.B = b.K + jB * Np; g.ldb = Np; g.sB = NN;
+      g.n_tiles = 1; g.K = (int)jB; g.lower_only = 0;
+      launch_gemm(g, nth, s);
     }
-    // right-looking sweep for VT = L^-T on the (identity-initialised) array:
-    //   VT[0:(j+1)B, jblock] = VT[0:(j+1)B, jblock] W_jj^T          (in place)
-    //   VT[0:(j+1)B, r > j] -= VT[0:(j+1)B, jblock] L[r, jblock]^T
-    {
+    // (2) diagonal block
+    potf2_inv_kernel<<<nth, 256, potf2_smem, s>>>(b.K + jB * (Np + 1), NN, Np,
+                                                  b.Winv + jB * NB, sWinv,
+                                                  b.VT + jB * (Np + 1), NN, (int)jB, b.info);
+    GPRY_CUDA(cudaGetLastError());
+    // (3) panel solve and the new block column of V^T, sharing the B operand W_jj
+    if (nb - j - 1 > 0 || j > 0) {
       GemmArgs g{};
-      g.A = b.VT + (size_t)j * NB;
-      g.lda = Np;
-      g.B = Wj;
-      g.ldb = NB;
-      g.C = b.VT + (size_t)j * NB;
-      g.ldc = Np;
-      g.M = (j + 1) * NB; g.N = NB; g.K = NB;
-      g.alpha = 1.0; g.accumulate = 0; g.filter = G_FILTER_ALL; g.klo_mode = G_KLO_ZERO;
-      launch_gemm(g, s);
-      if (rem > 0) {
-        GemmArgs u{};
-        u.A = b.VT + (size_t)j * NB; u.lda = Np;
-        u.B = b.K + (size_t)(j + 1) * NB * Np + (size_t)j * NB; u.ldb = Np;
-        u.C = b.VT + (size_t)(j + 1) * NB; u.ldc = Np;
-        u.M = (j + 1) * NB; u.N = rem; u.K = NB;
-        u.alpha = -1.0; u.accumulate = 1; u.filter = G_FILTER_ALL; u.klo_mode = G_KLO_ZERO;
-        launch_gemm(u, s);
-      }
+      double* panel = b.K + (jB + NB) * Np + jB;
+      g.seg[0] = GemmSeg{panel, panel, Np, Np, nb - j - 1, 1.0, 0, 0, NN, NN};
+      g.seg[1] = GemmSeg{b.TT, b.VT + jB, NB, Np, j, -1.0, 0, 0, sTT, NN};
+      g.B = b.Winv + jB * NB; g.ldb = NB; g.sB = sWinv;
+      g.n_tiles = 1; g.K = NB; g.lower_only = 0;
+      launch_gemm(g, nth, s);
     }
   }
   // alpha = V^T (V y)
-  gemv_vt_t_kernel<<<Np / 32, 256, 0, s>>>(b.VT, Np, N, b.y, b.t);
+  gemv_vt_t_kernel<<<dim3(Np / 32, nth), 256, 0, s>>>(b.VT, Np, N, b.y, b.t);
   GPRY_CUDA(cudaGetLastError());
-  gemv_vt_kernel<<<(Np * 32 + 255) / 256, 256, 0, s>>>(b.VT, Np, N, b.t, b.alpha);
+  gemv_vt_kernel<<<dim3((Np * 32 + 255) / 256, nth), 256, 0, s>>>(b.VT, Np, N, b.t, b.alpha);
   GPRY_CUDA(cudaGetLastError());
-  lml_scalars_kernel<<<1, 256, 0, s>>>(b.K, Np, N, b.y, b.alpha, b.scal);
+  lml_scalars_kernel<<<nth, 256, 0, s>>>(b.K, Np, N, b.y, b.alpha, b.scal);
   GPRY_CUDA(cudaGetLastError());
   if (need_grad) {
     // K^-1 = V^T V = VT VT^T (lower tiles; VT upper triangular: k >= tile row)
     GemmArgs g{};
-    g.A = b.VT; g.lda = Np; g.B = b.VT; g.ldb = Np; g.C = b.W; g.ldc = Np;
-    g.M = Np; g.N = Np; g.K = Np;
-    g.alpha = 1.0; g.accumulate = 0; g.filter = G_FILTER_LOWER; g.klo_mode = G_KLO_ROW;
-    launch_gemm(g, s);
+    g.seg[0] = GemmSeg{b.VT, b.W, Np, Np, nb, 1.0, 0, 1, NN, NN};
+    g.seg[1].m_tiles = 0;
+    g.B = b.VT; g.ldb = Np; g.sB = NN;
+    g.n_tiles = nb; g.K = Np; g.lower_only = 1;
+    launch_gemm(g, nth, s);
     const int nb32 = (N + 31) / 32;
     switch (kind) {
-      case GPRY_KERNEL_RBF: launch_grad<GPRY_KERNEL_RBF>(b, c, nb32, s); break;
-      case GPRY_KERNEL_MATERN15: launch_grad<GPRY_KERNEL_MATERN15>(b, c, nb32, s); break;
-      default: launch_grad<GPRY_KERNEL_MATERN25>(b, c, nb32, s);
+      case GPRY_KERNEL_RBF: launch_grad<GPRY_KERNEL_RBF>(b, nth, nb32, s); break;
+      case GPRY_KERNEL_MATERN15: launch_grad<GPRY_KERNEL_MATERN15>(b, nth, nb32, s); break;
+      default: launch_grad<GPRY_KERNEL_MATERN25>(b, nth, nb32, s);
     }
-    reduce_partials_kernel<<<d + 1, 256, 0, s>>>(b.partial, nb32 * nb32, d + 1, b.grad);
+    reduce_partials_kernel<<<dim3(P, nth), 256, 0, s>>>(b.partial, nb32 * nb32, P, b.grad);
     GPRY_CUDA(cudaGetLastError());
   }
+}
+
+// thetas per sub-batch: bounded by memory (3 Np^2 doubles each) and by what fills the GPU
+static int sub_batch(int B, int Np, bool need_grad) {
+  const double per_theta = (need_grad ? 3.0 : 2.0) * Np * (double)Np * 8.0;
+  int cap = (int)std::max(1.0, std::floor(16e9 / per_theta));
+  return std::max(1, std::min(std::min(B, 16), cap));
 }
 
 void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,
@@ -808,14 +830,13 @@ void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_tr
   GPRY_CHECK_ARG(N >= 1 && d >= 1 && d <= MAX_DIM, "need N >= 1 and 1 <= d <= 128");
   GPRY_CUDA(cudaSetDevice(st->device));
   st->f_valid = false;
-  TrainBuffers b = carve(st, 0, N, d, false, 1);
-  cudaStream_t s = b.stream;
-  upload_problem(st, b, X_train_t, noise2, y_t, s);
-  b.ell = upload_ells(st, b, theta, 1, s);
-  factorize_on_device(st, b, kind, theta, false, s);
-  int h_info[2] = {0, 0};
+  cudaStream_t s = 0;
+  TrainBuffers b = carve(st, N, d, false, 1);
+  upload_problem(b, X_train_t, noise2, y_t, s);
+  factorize_batch(st, b, kind, theta, 1, false, s);
+  int h_info = 0;
   double scal[2];
-  GPRY_CUDA(cudaMemcpyAsync(h_info, b.info, 8, cudaMemcpyDeviceToHost, s));
+  GPRY_CUDA(cudaMemcpyAsync(&h_info, b.info, sizeof(int), cudaMemcpyDeviceToHost, s));
   GPRY_CUDA(cudaMemcpyAsync(scal, b.scal, 16, cudaMemcpyDeviceToHost, s));
   if (out_alpha) GPRY_CUDA(cudaMemcpyAsync(out_alpha, b.alpha, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
   if (out_L || out_V) {
@@ -833,9 +854,9 @@ void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_tr
     }
   }
   GPRY_CUDA(cudaStreamSynchronize(s));
-  *info = h_info[0];
+  *info = h_info;
   if (out_logdet_half) *out_logdet_half = scal[0];
-  if (keep && h_info[0] == 0) {
+  if (keep && h_info == 0) {
     st->f_valid = true;
     st->f_N = N;
     st->f_d = d;
@@ -843,9 +864,6 @@ void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_tr
   }
 }
 
-// B hyper-parameter vectors are evaluated round-robin on up to MAX_TRAIN_STREAMS streams with
-// private work sets, so that the latency-bound diagonal-block kernels of one evaluation
-// overlap the GEMMs of the others.  Per-theta results land in pinned host memory.
 void lml_batched_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                         const double* noise2, const double* y_t, const double* thetas, int B,
                         double* out_lml, double* out_grad, int* out_info) {
@@ -853,57 +871,41 @@ void lml_batched_device(gpry_state* st, int kind, int N, int d, const double* X_
   GPRY_CHECK_ARG(N >= 1 && d >= 1 && d <= MAX_DIM, "need N >= 1 and 1 <= d <= 128");
   GPRY_CUDA(cudaSetDevice(st->device));
   st->f_valid = false;
+  cudaStream_t s = 0;
   const bool need_grad = out_grad != nullptr;
   const int P = d + 1;
-  const int nset = std::min(B, MAX_TRAIN_STREAMS);
-  std::vector<TrainBuffers> sets;
-  for (int i = 0; i < nset; i++) sets.push_back(carve(st, i, N, d, need_grad, B));
-  // f_prob may have been reallocated by a later carve: refresh the shared pointers
-  for (auto& b : sets) {
-    b.y = st->f_prob.p;
-    b.noise2 = b.y + b.Np;
-    b.X = b.noise2 + b.Np;
-  }
-  const size_t rec = (size_t)P + 4;   // per theta: [info][logdet_half][y.alpha][pad][grad P]
-  if (st->f_pinned_cap < rec * B) {
-    if (st->f_pinned) cudaFreeHost(st->f_pinned);
-    st->f_pinned = nullptr;
-    GPRY_CUDA(cudaMallocHost((void**)&st->f_pinned, rec * B * sizeof(double)));
-    st->f_pinned_cap = rec * B;
-  }
-  if (!st->f_evt) GPRY_CUDA(cudaEventCreateWithFlags(&st->f_evt, cudaEventDisableTiming));
-  upload_problem(st, sets[0], X_train_t, noise2, y_t, sets[0].stream);
-  double* ells = upload_ells(st, sets[0], thetas, B, sets[0].stream);
-  GPRY_CUDA(cudaEventRecord(st->f_evt, sets[0].stream));
-  for (int i = 1; i < nset; i++) GPRY_CUDA(cudaStreamWaitEvent(sets[i].stream, st->f_evt, 0));
-  for (int i = 0; i < B; i++) {
-    TrainBuffers& b = sets[i % nset];
-    cudaStream_t s = b.stream;
-    b.ell = ells + (size_t)i * MAX_DIM;
-    factorize_on_device(st, b, kind, thetas + (size_t)i * P, need_grad, s);
-    double* r = st->f_pinned + rec * i;
-    GPRY_CUDA(cudaMemcpyAsync(r, b.info, 8, cudaMemcpyDeviceToHost, s));
-    GPRY_CUDA(cudaMemcpyAsync(r + 1, b.scal, 16, cudaMemcpyDeviceToHost, s));
-    if (need_grad) GPRY_CUDA(cudaMemcpyAsync(r + 4, b.grad, P * 8, cudaMemcpyDeviceToHost, s));
-  }
-  for (int i = 0; i < nset; i++) GPRY_CUDA(cudaStreamSynchronize(sets[i].stream));
-  for (int i = 0; i < B; i++) {
-    const double* r = st->f_pinned + rec * i;
-    const int h_info = *reinterpret_cast<const int*>(r);
-    out_info[i] = h_info;
-    if (h_info != 0) {   // sklearn:_gpr.py:592-593
-      out_lml[i] = -INFINITY;
-      if (need_grad)
-        for (int p = 0; p < P; p++) out_grad[(size_t)i * P + p] = 0.0;
-      continue;
-    }
-    // -0.5 y^T alpha - sum(log diag L) - N/2 log(2 pi)        (sklearn:_gpr.py:613-617)
-    double lml = -0.5 * r[2];
-    lml -= r[1];
-    lml -= N / 2.0 * log(2.0 * M_PI);
-    out_lml[i] = lml;
+  const int Bs = sub_batch(B, round_up(N, NB), need_grad);
+  TrainBuffers b = carve(st, N, d, need_grad, Bs);
+  upload_problem(b, X_train_t, noise2, y_t, s);
+  std::vector<int> h_info(Bs);
+  std::vector<double> h_scal(2 * (size_t)Bs), h_grad((size_t)(MAX_DIM + 8) * Bs);
+  for (int i0 = 0; i0 < B; i0 += Bs) {
+    const int nth = std::min(Bs, B - i0);
+    factorize_batch(st, b, kind, thetas + (size_t)i0 * P, nth, need_grad, s);
+    GPRY_CUDA(cudaMemcpyAsync(h_info.data(), b.info, (size_t)nth * sizeof(int),
+                              cudaMemcpyDeviceToHost, s));
+    GPRY_CUDA(cudaMemcpyAsync(h_scal.data(), b.scal, (size_t)nth * 16, cudaMemcpyDeviceToHost, s));
     if (need_grad)
-      for (int p = 0; p < P; p++) out_grad[(size_t)i * P + p] = r[4 + p];
+      GPRY_CUDA(cudaMemcpyAsync(h_grad.data(), b.grad, (size_t)nth * (MAX_DIM + 8) * 8,
+                                cudaMemcpyDeviceToHost, s));
+    GPRY_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < nth; i++) {
+      const int gi = i0 + i;
+      out_info[gi] = h_info[i];
+      if (h_info[i] != 0) {   // sklearn:_gpr.py:592-593
+        out_lml[gi] = -INFINITY;
+        if (need_grad)
+          for (int p = 0; p < P; p++) out_grad[(size_t)gi * P + p] = 0.0;
+        continue;
+      }
+      // -0.5 y^T alpha - sum(log diag L) - N/2 log(2 pi)        (sklearn:_gpr.py:613-617)
+      double lml = -0.5 * h_scal[2 * i + 1];
+      lml -= h_scal[2 * i];
+      lml -= N / 2.0 * log(2.0 * M_PI);
+      out_lml[gi] = lml;
+      if (need_grad)
+        for (int p = 0; p < P; p++) out_grad[(size_t)gi * P + p] = h_grad[(size_t)i * (MAX_DIM + 8) + p];
+    }
   }
 }
 
