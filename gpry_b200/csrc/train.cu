@@ -153,11 +153,16 @@ __device__ __forceinline__ void store_acc(double* __restrict__ C, const double (
     }
 }
 
-// One warp: Cholesky of the 32 x 32 block D (lane = row, row in registers, right-looking) and
-// its inverse (lane = column, forward substitution); writes L (upper zeroed) back into D and
-// the inverse into Winv.
+// One warp: Cholesky of the 32 x 32 block D (lane = row, the row lives in registers,
+// right-looking; the pivot column is broadcast through a 32-double shared buffer) and its
+// inverse by forward substitution (lane = column; L is re-read from shared memory as
+// broadcast loads).  1 / L_kk comes from rsqrt, so the loop has no sqrt / division chain.
+// Writes L (upper zeroed) back into D and the inverse into Winv.  scratch: 96 doubles.
 __device__ __forceinline__ void factor_inv_32(double* __restrict__ D, double* __restrict__ Winv,
-                                              int lane, int pivot_offset, int* __restrict__ info) {
+                                              double* __restrict__ scratch, int lane,
+                                              int pivot_offset, int* __restrict__ info) {
+  double* col = scratch;          // [2][32] pivot column, double buffered
+  double* invd = scratch + 64;    // [32]    1 / L_kk
   double a[SB];
 #pragma unroll
   for (int k = 0; k < SB; k++) a[k] = D[lane * SBLD + k];
@@ -168,33 +173,47 @@ __device__ __forceinline__ void factor_inv_32(double* __restrict__ D, double* __
       if (lane == 0 && *info == 0) *info = pivot_offset + k + 1;
       dkk = 1.0;
     }
-    const double sq = sqrt(dkk);
-    const double lk = (lane == k) ? sq : a[k] / sq;
+    // 1/sqrt and sqrt to < 1 ulp (one Newton step each), then a / sqrt(d) as a correctly
+    // rounded quotient by residual correction: no sqrt / division latency chain
+    double rs = rsqrt(dkk);
+    rs = fma(rs * 0.5, fma(-dkk * rs, rs, 1.0), rs);
+    double sq = dkk * rs;
+    sq = fma(fma(-sq, sq, dkk), 0.5 * rs, sq);
+    double q = a[k] * rs;
+    q = fma(fma(-q, sq, a[k]), rs, q);
+    const double lk = (lane == k) ? sq : q;
     a[k] = lk;
+    double* cb = col + (k & 1) * 32;
+    cb[lane] = lk;
+    if (lane == k) invd[k] = rs;
+    __syncwarp();
 #pragma unroll
     for (int j = k + 1; j < SB; j++) {
-      double ljk = __shfl_sync(0xffffffffu, lk, j);
+      const double ljk = cb[j];
       if (lane >= j) a[j] = fma(-lk, ljk, a[j]);
     }
   }
-  // inverse: lane c holds column c of W
+#pragma unroll
+  for (int k = 0; k < SB; k++) D[lane * SBLD + k] = (k <= lane) ? a[k] : 0.0;
+  __syncwarp();
+  // inverse: lane c holds column c of W;  w_i = (delta_ic - sum_{m<i} L_im w_m) / L_ii
   double w[SB];
 #pragma unroll
   for (int i = 0; i < SB; i++) {
-    double s = (i == lane) ? 1.0 : 0.0;
+    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
 #pragma unroll
-    for (int m = 0; m < i; m++) {
-      double lim = __shfl_sync(0xffffffffu, a[m], i);
-      s = fma(-lim, w[m], s);
+    for (int m = 0; m + 1 < i; m += 2) {
+      s0 = fma(-D[i * SBLD + m], w[m], s0);
+      s1 = fma(-D[i * SBLD + m + 1], w[m + 1], s1);
     }
-    double lii = __shfl_sync(0xffffffffu, a[i], i);
-    w[i] = (i >= lane) ? s / lii : 0.0;
+    if (i & 1) s0 = fma(-D[i * SBLD + i - 1], w[i - 1], s0);
+    const double si = s0 + s1, ri = invd[i];
+    double wq = si * ri;
+    wq = fma(fma(-wq, D[i * SBLD + i], si), ri, wq);     // si / L_ii by residual correction
+    w[i] = (i >= lane) ? wq : 0.0;
   }
 #pragma unroll
-  for (int k = 0; k < SB; k++) {
-    D[lane * SBLD + k] = (k <= lane) ? a[k] : 0.0;
-    Winv[k * SBLD + lane] = w[k];
-  }
+  for (int k = 0; k < SB; k++) Winv[k * SBLD + lane] = w[k];
 }
 
 __global__ void __launch_bounds__(256)
@@ -218,8 +237,8 @@ potf2_inv_kernel(double* __restrict__ Aall, size_t sA, int ld, double* __restric
   double acc[4][4][2];
   for (int kb = 0; kb < 4; kb++) {
     if (warp == 0)
-      factor_inv_32(Lb + sbidx(kb, kb) * SB_DOUBLES, Wb + sbidx(kb, kb) * SB_DOUBLES, lane,
-                    row_offset + kb * SB, info);
+      factor_inv_32(Lb + sbidx(kb, kb) * SB_DOUBLES, Wb + sbidx(kb, kb) * SB_DOUBLES,
+                    sh + 20 * SB_DOUBLES, lane, row_offset + kb * SB, info);
     __syncthreads();
     // panel: L[ib][kb] = A[ib][kb] * W_kk^T
     if (warp < 3 - kb) {
@@ -757,7 +776,7 @@ static void factorize_batch(gpry_state* st, TrainBuffers& b, int kind, const dou
     default: launch_kmat<GPRY_KERNEL_MATERN25>(b, nth, s);
   }
   gemm_prepare();
-  const size_t potf2_smem = 20 * (size_t)SB_DOUBLES * 8;
+  const size_t potf2_smem = (20 * (size_t)SB_DOUBLES + 96) * 8;
   GPRY_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)potf2_smem));
   const size_t sWinv = (size_t)nb * NB * NB, sTT = (size_t)Np * NB;
