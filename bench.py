@@ -47,6 +47,7 @@ def parse_args():
     p.add_argument("--cpu-chunk", type=int, default=20000)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-secondary", action="store_true")
     return p.parse_args()
 
 
@@ -220,6 +221,46 @@ def fit_state_for_bench(dev, N, d):
                  y_mean=y_mean, y_std=y_std, clip_hi=clip_hi, y_max=float(y.max()),
                  noise_level=noise_level, zeta=float(d) ** -0.85)
     return model
+
+
+def secondary_figures(dev, dev_t):
+    """BASELINE.json configs[3] and configs[4] on one GPU (device-event timed)."""
+    import torch
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # config D: LML + gradient, N_train = 4000, d = 20, 8 restarts' worth of theta per call
+    N, d, B = 4000, 20, 8
+    X, y, theta, bounds = synthetic_problem(N, d)
+    y_ = (y - y.mean()) / y.std()
+    noise2 = np.full(N, (1e-2 / y.std()) ** 2)
+    thetas = theta + 0.1 * np.random.default_rng(7).standard_normal((B, d + 1))
+    dev.lml_batched("rbf", X, noise2, y_, thetas[:2])
+    t0 = time.perf_counter()
+    lml, grad, info = dev.lml_batched("rbf", X, noise2, y_, thetas)
+    dt = time.perf_counter() - t0
+    flop = N ** 3 + (3 * d + 4 + 2 * (d + 1)) * N ** 2 / 2      # SURVEY 8(d)
+    out["lml_grad"] = {"n_train": N, "dim": d, "batch": B, "evals_per_s": B / dt,
+                       "ms_per_eval": dt / B * 1e3, "tflops_algorithmic": flop * B / dt * 1e-12,
+                       "all_pd": bool(np.all(info == 0))}
+    # config E: mean-only proposals (surrogate MCMC), N_train = 2000, d = 16, 10^7 per step
+    N, d, M = 2000, 16, 10_000_000
+    model = fit_state_for_bench(dev, N, d)
+    dev.upload(model["kind"], model["X_"], model["alpha_"], model["V"], model["c"], model["ell"],
+               model["x_min"], model["x_width"], model["y_mean"], model["y_std"],
+               model["clip_hi"])
+    Xd = torch.rand((M, d), dtype=torch.float64, device=dev_t)
+    s = torch.cuda.current_stream()
+    dev.predict(Xd, return_std=False, stream=s)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        dev.predict(Xd, return_std=False, stream=s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    out["mean_only"] = {"n_train": N, "dim": d, "proposals_per_step": M,
+                        "proposals_per_s": M / ms * 1e3, "ms_per_step": ms}
+    return out
 
 
 def run_ours(args):
@@ -416,6 +457,12 @@ def run_ours(args):
                                       f"workload (N_train={N}, d={d}); best chunk {thr_best:.0f} "
                                       f"cand/s; BLAS={blas}; os.cpu_count={os.cpu_count()}"}
 
+    # ---- secondary figures of the same path (not the headline metric): LML+gradient
+    # evaluations/s at config D and mean-only proposals/s at config E, this GPU only ----
+    secondary = None
+    if rank == 0 and not args.no_secondary:
+        secondary = secondary_figures(dev, dev_t)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -429,6 +476,7 @@ def run_ours(args):
                        "state_bcast_ms": t_bcast_ms},
             "e2e": e2e, "gpu_launches": int(tm["launches"]), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "agreement": agreement, "clocks": clk,
+            "secondary": secondary,
         }
         print(json.dumps(line))
     if world > 1:

@@ -48,6 +48,7 @@ SIGNATURES = {
     "gpry_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
                             C.c_void_p, _c_int64_p, C.c_void_p]),
     "gpry_mean_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpry_std_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpry_posterior_cov": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p]),
     "gpry_kernel_cross": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -47,12 +47,26 @@ class LogExp:
     def __call__(self, X, gp, eval_gradient=False):
         """acquisition_functions.py:936-992: value; ``-inf`` where sigma^2 - sigma_n^2 <= 0 or
         the mean is not finite (classifier / trust-region rows)."""
-        if eval_gradient:
-            raise NotImplementedError(
-                "the gradient branch (BatchOptimizer, acquisition_functions.py:993-1007) is "
-                "not on the B200 hot path")
         X = np.atleast_2d(np.asarray(X, dtype=float))
         noise_var = self.noise_var(gp)
+        if eval_gradient:   # acquisition_functions.py:966-969, 993-1007 (one point)
+            mu, std, mu_grad, std_grad = gp.predict(X, return_std=True, return_mean_grad=True,
+                                                    return_std_grad=True)
+            var = std ** 2 - noise_var ** 2.
+            mask = (var > 0) & np.isfinite(mu)
+            values = np.where(mask, self.f(mu, std, gp.y_max, noise_var, self.zeta), -np.inf)
+            if np.array(std_grad).ndim > 1:
+                grad = np.zeros_like(std_grad)
+                if np.any(mask):
+                    grad[mask] = np.array(std_grad)[mask] / (std[mask] - noise_var) \
+                        + 2 * self.zeta * np.array(mu_grad)[mask]
+                if np.any(~mask):
+                    grad[~mask] = np.inf
+            elif std[0] > noise_var:
+                grad = std_grad / (std[0] - noise_var) + 2 * self.zeta * mu_grad
+            else:
+                grad = np.ones_like(std_grad) * np.inf
+            return values, grad
         if gp.infinities_classifier is None and gp.trust_bounds is None:
             mu, std, values = gp.predict_logexp(X, self.zeta, noise_var)
         else:  # masks are host-side: take mean/std through predict, then f on the host

@@ -294,6 +294,13 @@ int gpry_mean_grad(gpry_state* st, const double* x, double* out_grad) {
   });
 }
 
+int gpry_std_grad(gpry_state* st, const double* x, double* out_grad, double* out_std) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && x && out_grad, "NULL argument");
+    std_grad_device(st, x, out_grad, out_std);
+  });
+}
+
 int gpry_posterior_cov(gpry_state* st, const double* X, int Ka, int where, double* out_cov,
                        void* stream) {
   return guarded([&] {

@@ -989,4 +989,138 @@ void kernel_gradx_device(gpry_state* st, const double* x_host, double* out_host)
   GPRY_CUDA(cudaStreamSynchronize(s));
 }
 
+// ---------------------------------------------------------------------------------------
+// std gradient at one point (gpr.py:1247-1261):
+//   grad_std = -(k*^T V^T V dk*/dx) / sqrt(var_)  then  * y_std * y_std  (the reference applies
+//   inverse_transform_scale twice).  u = V k*, z = V^T u, grad_k = sum_j z_j dk*_j/dx_k.
+// ---------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void kstar_single_kernel(const double* __restrict__ T, int N, int Np, int DP,
+                                    const double* __restrict__ u_scaled, double c,
+                                    double* __restrict__ ks) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Np) return;
+  double v = 0.0;
+  if (j < N) {
+    double r2 = 0.0;
+    for (int k = 0; k < DP; k++) {
+      double df = u_scaled[k] - T[(size_t)j * DP + k];
+      r2 = fma(df, df, r2);
+    }
+    v = kernel_value<KIND>(r2, c);
+  }
+  ks[j] = v;
+}
+// u = V k*  (V row major lower, warp per row)
+__global__ void gemv_lower_kernel(const double* __restrict__ V, int Np, int N,
+                                  const double* __restrict__ x, double* __restrict__ y) {
+  int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (j >= Np) return;
+  double s = 0.0;
+  if (j < N)
+    for (int k = lane; k <= j; k += 32) s = fma(V[(size_t)j * Np + k], x[k], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) y[j] = s;
+}
+// z = V^T u  (CTA per 32 columns, 8 row groups, fixed-order sums)
+__global__ void __launch_bounds__(256)
+gemv_lower_t_kernel(const double* __restrict__ V, int Np, int N, const double* __restrict__ u,
+                    double* __restrict__ z) {
+  __shared__ double red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + cx;
+  double s = 0.0;
+  if (k < N)
+    for (int j = blockIdx.x * 32 + ry; j < N; j += 8)
+      if (j >= k) s = fma(V[(size_t)j * Np + k], u[j], s);
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0) {
+    double v = 0.0;
+    for (int q = 0; q < 8; q++) v += red[q][cx];
+    if (k < Np) z[k] = v;
+  }
+}
+// scale[0] = -y_std^2 / sqrt(max(c - |u|^2, 0))   (0 if the variance vanishes)
+__global__ void std_grad_scale_kernel(const double* __restrict__ u, int N, double c, double y_std,
+                                      double* __restrict__ out) {
+  __shared__ double r[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) s = fma(u[i], u[i], s);
+  r[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) r[threadIdx.x] += r[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double var = c - r[0];
+    out[0] = var > 0.0 ? -(y_std * y_std) / sqrt(var) : 0.0;
+    out[1] = var > 0.0 ? sqrt(var) * y_std : 0.0;
+  }
+}
+__global__ void scale_vec_kernel(double* __restrict__ v, int n, const double* __restrict__ scale) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] *= scale[0];
+}
+
+void std_grad_device(gpry_state* st, const double* x_host, double* out_grad, double* out_std) {
+  if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+  GPRY_CUDA(cudaSetDevice(st->device));
+  const int d = st->d, N = st->N, Np = st->Npad, DP = st->DP;
+  cudaStream_t s = 0;
+  // host: transformed point x_ and scaled point x_ / ell (same expressions as the device path)
+  std::vector<double> prm(3 * MAX_DIM);
+  GPRY_CUDA(cudaMemcpy(prm.data(), st->prm_dev.p, 3 * MAX_DIM * 8, cudaMemcpyDeviceToHost));
+  std::vector<double> buf(MAX_DIM + DP, 0.0);
+  for (int k = 0; k < d; k++) {
+    double xt = (x_host[k] - prm[k]) / prm[MAX_DIM + k];
+    buf[k] = xt;                                   // transformed (gradient kernel)
+    buf[MAX_DIM + k] = xt / prm[2 * MAX_DIM + k];  // scaled (kernel values)
+  }
+  st->small.reserve(4 * MAX_DIM + 8);
+  st->pc_U.reserve(3 * (size_t)Np);
+  double* d_xt = st->small.p;                 // [MAX_DIM]
+  double* d_us = st->small.p + MAX_DIM;       // [DP]
+  double* d_out = st->small.p + 2 * MAX_DIM;  // [MAX_DIM]
+  double* d_scale = st->small.p + 3 * MAX_DIM;
+  double *ks = st->pc_U.p, *u = ks + Np, *z = u + Np;
+  GPRY_CUDA(cudaMemcpyAsync(d_xt, buf.data(), (MAX_DIM + DP) * 8, cudaMemcpyHostToDevice, s));
+  const int nblk = (Np + 255) / 256;
+  switch (st->kind) {
+    case GPRY_KERNEL_RBF:
+      kstar_single_kernel<GPRY_KERNEL_RBF><<<nblk, 256, 0, s>>>(st->T.p, N, Np, DP, d_us, st->c, ks);
+      break;
+    case GPRY_KERNEL_MATERN15:
+      kstar_single_kernel<GPRY_KERNEL_MATERN15><<<nblk, 256, 0, s>>>(st->T.p, N, Np, DP, d_us, st->c, ks);
+      break;
+    default:
+      kstar_single_kernel<GPRY_KERNEL_MATERN25><<<nblk, 256, 0, s>>>(st->T.p, N, Np, DP, d_us, st->c, ks);
+  }
+  GPRY_CUDA(cudaGetLastError());
+  gemv_lower_kernel<<<(Np * 32 + 255) / 256, 256, 0, s>>>(st->Vrm.p, Np, N, ks, u);
+  GPRY_CUDA(cudaGetLastError());
+  gemv_lower_t_kernel<<<Np / 32, 256, 0, s>>>(st->Vrm.p, Np, N, u, z);
+  GPRY_CUDA(cudaGetLastError());
+  std_grad_scale_kernel<<<1, 256, 0, s>>>(u, N, st->c, st->y_std, d_scale);
+  GPRY_CUDA(cudaGetLastError());
+  const double* ell = st->prm_dev.p + 2 * MAX_DIM;
+  switch (st->kind) {   // sum_j z_j dk*_j/dx_k   (y_std factor 1: the scale carries y_std^2)
+    case GPRY_KERNEL_RBF:
+      mean_grad_kernel<GPRY_KERNEL_RBF><<<d, 256, 0, s>>>(st->Xt.p, z, N, d, d_xt, ell, st->c, 1.0, d_out);
+      break;
+    case GPRY_KERNEL_MATERN15:
+      mean_grad_kernel<GPRY_KERNEL_MATERN15><<<d, 256, 0, s>>>(st->Xt.p, z, N, d, d_xt, ell, st->c, 1.0, d_out);
+      break;
+    default:
+      mean_grad_kernel<GPRY_KERNEL_MATERN25><<<d, 256, 0, s>>>(st->Xt.p, z, N, d, d_xt, ell, st->c, 1.0, d_out);
+  }
+  GPRY_CUDA(cudaGetLastError());
+  scale_vec_kernel<<<1, MAX_DIM, 0, s>>>(d_out, d, d_scale);
+  GPRY_CUDA(cudaGetLastError());
+  GPRY_CUDA(cudaMemcpyAsync(out_grad, d_out, d * 8, cudaMemcpyDeviceToHost, s));
+  if (out_std) GPRY_CUDA(cudaMemcpyAsync(out_std, d_scale + 1, 8, cudaMemcpyDeviceToHost, s));
+  GPRY_CUDA(cudaStreamSynchronize(s));
+}
+
 }  // namespace gpry

@@ -130,6 +130,7 @@ void posterior_cov_device(gpry_state* st, const double* dX, int Ka, double* d_ou
 void kernel_cross_device(gpry_state* st, int kind, int d, const double* theta, const double* hX,
                          int M, const double* hY, int N, double* h_out);
 void kernel_gradx_device(gpry_state* st, const double* x_host, double* out_host);
+void std_grad_device(gpry_state* st, const double* x_host, double* out_grad, double* out_std);
 // topk.cu
 int64_t topk_device(gpry_state* st, const double* d_scores, int64_t M, int Kp, int64_t idx_base,
                     double** d_keys_out, int64_t** d_idx_out, cudaStream_t s);

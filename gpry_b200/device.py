@@ -188,6 +188,16 @@ class DeviceGP:
         check(self._lib.gpry_mean_grad(self._h, ptr(x), ptr(out)))
         return out
 
+    def std_grad(self, x):
+        """(d std/dx_ (d,), std) at one un-transformed point (gpr.py:1247-1261)."""
+        x = as_f64(x).reshape(-1)
+        if x.size != self.d:
+            raise ValueError(f"x must have {self.d} entries")
+        out = np.empty(self.d)
+        std = C.c_double(0.0)
+        check(self._lib.gpry_std_grad(self._h, ptr(x), ptr(out), C.byref(std)))
+        return out, std.value
+
     def posterior_cov(self, X, stream=None):
         """Posterior covariance (normalised units, no noise) among the rows of X (Ka <= 8192)."""
         X, Ka, where = self._prep_X(X)

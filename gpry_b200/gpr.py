@@ -649,10 +649,6 @@ class GaussianProcessRegressor:
                              "mean grad.")
         if X.shape[0] != 1 and (return_mean_grad or return_std_grad):
             raise ValueError("Mean grad and std grad not implemented for n_samples > 1")
-        if return_std_grad:
-            raise NotImplementedError(
-                "return_std_grad (BatchOptimizer path, gpr.py:1247-1266) is not on the B200 "
-                "hot path yet; see DESIGN.md 'next rows'")
         X = self._as_2d(X, validate)
         impose_trust_region = self.trust_bounds is not None and not ignore_trust_region
         i_outside_trust = None
@@ -665,6 +661,7 @@ class GaussianProcessRegressor:
             y_mean_full = np.ones(n_samples)
             y_std_full = np.zeros(n_samples)
             grad_mean_full = np.ones((n_samples, n_dims))
+            grad_std_full = np.zeros((n_samples, n_dims))
             X_ = self.preprocessing_X.transform(X)
             finite = self.infinities_classifier.predict(np.ascontiguousarray(X_),
                                                         validate=validate)
@@ -675,6 +672,8 @@ class GaussianProcessRegressor:
                     out.append(np.zeros(n_samples))
                 if return_mean_grad:
                     out.append(np.ones((n_samples, n_dims)) * self.inf_value)
+                if return_std_grad:
+                    out.append(np.zeros((n_samples, n_dims)))
                 return out[0] if len(out) == 1 else tuple(out)
             y_mean_full[~finite] = self.minus_inf_value
             grad_mean_full[~finite] = self.inf_value
@@ -697,6 +696,14 @@ class GaussianProcessRegressor:
             if finite is not None:
                 grad_mean_full[finite] = grad_mean
                 grad_mean = grad_mean_full
+            if return_std_grad:   # gpr.py:1247-1266
+                grad_std = np.zeros(X.shape[1])
+                if not np.allclose(y_std, grad_std):
+                    grad_std, _ = dev.std_grad(X[0])
+                    if finite is not None:
+                        grad_std_full[finite] = grad_std
+                        grad_std = grad_std_full
+                return y_mean, y_std, grad_mean, grad_std
             if return_std:
                 return y_mean, y_std, grad_mean
             return y_mean, grad_mean

@@ -135,6 +135,11 @@ int gpry_topk(gpry_state* st, const double* scores, int64_t M, int Kp, int where
  * gradient is w.r.t. the transformed coordinate, scaled by y_std (gpr.py:1237-1242). */
 int gpry_mean_grad(gpry_state* st, const double* x, double* out_grad);
 
+/* d std / d x_ at ONE un-transformed point x (d) -> out_grad (d); out_std (1, may be NULL)
+ * receives the std at x.  gpr.py:1247-1261: -(kstar^T V^T V dkstar_dx) / sqrt(var_), multiplied by
+ * y_std twice as the reference does; zero if the variance vanishes.  Host pointers. */
+int gpry_std_grad(gpry_state* st, const double* x, double* out_grad, double* out_std);
+
 /*
  * Posterior covariance (normalised units, prior variance c on the diagonal minus the explained
  * part, NO noise term) among Ka <= 8192 candidates X (Ka x d, un-transformed):

@@ -54,13 +54,42 @@ def test_predict_like_reference(golden):
     assert abs(gpr.y_max - float(g["y_max"])) == 0
 
 
+def test_std_grad_like_reference(golden):
+    from gpry_b200.acquisition_functions import LogExp
+    g = golden
+    gpr = make_gpr(g)
+    m, s, gm, gs = gpr.predict(g["Xc"][:1], return_std=True, return_mean_grad=True,
+                               return_std_grad=True)
+    assert scaled_err(gs, g["grad_std"], np.abs(g["grad_std"]).max()) < 1e-8
+    assert scaled_err(gm, g["grad_mean"], np.abs(g["grad_mean"]).max()) < TOL
+    # finite-difference check of the LogExp gradient in the transformed coordinate
+    acq = LogExp(zeta=g["zeta"])
+    val, grad = acq(g["Xc"][:1], gpr, eval_gradient=True)
+    if np.isfinite(val[0]):
+        width = (g["bounds"][:, 1] - g["bounds"][:, 0]) if g["normalize"] else np.ones(g["d"])
+        sy = float(g["y_std"])
+        k, h = 0, 1e-6
+        xp, xm = g["Xc"][:1].copy(), g["Xc"][:1].copy()
+        xp[0, k] += h * width[k]
+        xm[0, k] -= h * width[k]
+        mu_p, sd_p = gpr.predict(xp, return_std=True)
+        mu_m, sd_m = gpr.predict(xm, return_std=True)
+        # the reference's formula: std_grad / (std - sigma_n) + 2 zeta mu_grad, where std_grad
+        # carries an extra factor y_std (inverse_transform_scale applied twice, gpr.py:1257-1261)
+        fd = ((sd_p[0] - sd_m[0]) / (2 * h)) * sy / (s[0] - g["noise_level"]) \
+            + 2 * g["zeta"] * (mu_p[0] - mu_m[0]) / (2 * h)
+        assert abs(grad[k] - fd) < 1e-4 * max(1.0, abs(fd))
+
+
 def test_errors_like_reference(golden):
     gpr = make_gpr(golden)
     X = golden["Xc"]
     with pytest.raises(ValueError):
-        gpr.predict(X[:1], return_std_grad=True)
+        gpr.predict(X[:1], return_std_grad=True)          # needs std and mean grad too
     with pytest.raises(ValueError):
         gpr.predict(X[:2], return_mean_grad=True)
+    with pytest.raises(ValueError):
+        gpr.predict(X[:2], return_std=True, return_mean_grad=True, return_std_grad=True)
 
 
 def test_logexp_call(golden):
