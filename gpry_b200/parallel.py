@@ -188,3 +188,37 @@ def best_fit_across_processes(lml, theta):
     out = out.cpu().numpy().reshape(size(), -1)
     best = int(np.argmax(out[:, 0]))
     return float(out[best, 0]), out[best, 1:].copy(), best
+
+
+def fit_gpr_parallel(gpr, new_X, new_y, n_restarts=None, hyperparameter_bounds=None):
+    """Restart-parallel hyper-parameter fit, ``Runner._fit_gpr_parallel`` (run.py:1238-1301).
+
+    Every rank holds the same regressor and receives the same new points.  The restarts are
+    split with ``split_number_for_parallel_processes`` (run.py:1254); only rank 0 starts its
+    first run from the current theta (run.py:1250); each rank fits its share on its own GPU
+    (lock-step batched LML evaluations).  Instead of broadcasting the pickled winner
+    (``_share_gpr``, run.py:749-756, N^2 factors included) the ranks all-gather
+    (lml, theta) and every rank re-factorises the winning theta locally, which leaves all
+    ranks with identical state.  Returns the rank that produced the winner.
+    """
+    n_total = gpr.n_restarts_optimizer if n_restarts is None else n_restarts
+    mine = int(split_number_for_parallel_processes(n_total)[rank()])
+    if mine or is_main_process():
+        gpr.append_to_data(
+            new_X, new_y, fit_classifier=True,
+            fit_gpr=({"n_restarts": mine, "start_from_current": is_main_process(),
+                      "hyperparameter_bounds": hyperparameter_bounds} if mine else False))
+        lml = gpr.log_marginal_likelihood_value_ if mine else -np.inf
+    else:   # no run assigned: still add the points (kept-constant hyper-parameters)
+        gpr.append_to_data(new_X, new_y, fit_classifier=True, fit_gpr=False)
+        lml = -np.inf
+    theta = gpr.kernel_.theta
+    best_lml, best_theta, best_rank = best_fit_across_processes(lml, theta)
+    if multiple_processes() and np.isfinite(best_lml):
+        if not np.array_equal(best_theta, theta):
+            gpr.kernel_.theta = best_theta
+            gpr.newly_appended_for_inv = max(gpr.newly_appended_for_inv, 1)
+            gpr._update_model()
+        gpr.log_marginal_likelihood_value_ = best_lml
+        gpr._fitted = True
+    return best_rank

@@ -1,0 +1,69 @@
+"""2-GPU test (NCCL): restart-parallel fit leaves every rank with the same, best model, and the
+sharded NORA ranking equals the single-process ranking.  Skipped with fewer than 2 GPUs."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    from conftest import golden_pool_candidates, load_golden
+    from gpry_b200 import parallel
+    from gpry_b200.acquisition_functions import LogExp
+    from gpry_b200.gp_acquisition import NORA
+    from gpry_b200.gpr import GaussianProcessRegressor
+    from gpry_b200.preprocessing import Normalize_bounds, Normalize_y
+    from test_gpu_gpr import make_gpr
+    # --- restart-parallel fit
+    z = np.load(os.path.join(root, "tests", "golden", "fit_rbf_d2_n40.npz"))
+    gpr = GaussianProcessRegressor(
+        kernel="RBF", bounds=z["bounds"], noise_level=1e-2, n_restarts_optimizer=6,
+        preprocessing_X=Normalize_bounds(z["bounds"]), preprocessing_y=Normalize_y(),
+        account_for_inf=None, random_state=100 + rank, verbose=0)
+    best_rank = parallel.fit_gpr_parallel(gpr, z["X_train"], z["y_train"])
+    thetas = parallel.allgather(gpr.kernel_.theta)
+    assert all(np.array_equal(t, thetas[0]) for t in thetas)
+    assert gpr.fitted and np.isfinite(gpr.log_marginal_likelihood_value_)
+    m = gpr.predict(z["Xc"])
+    ms = parallel.allgather(m)
+    assert all(np.array_equal(x, ms[0]) for x in ms)
+    # --- sharded NORA == golden single-process ranking
+    g = load_golden("rbf_d8_n300")
+    gpr2 = make_gpr(g)
+    Xp = golden_pool_candidates(g)
+    nora = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=128)
+    X_pool, y_pool, acq_pool = nora.multi_add(gpr2, n_points=int(g["pool_n_points"]), X_mc=Xp)
+    assert np.array_equal(X_pool, Xp[g["pool_idx_single_sort_acq"]])
+    np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.array([best_rank]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpus(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok_0.npy") and os.path.exists(tmp_path / "ok_1.npy")
