@@ -418,8 +418,18 @@ def run_ours(args):
         del a, b
     except Exception:
         pass
+    traffic, traffic_src = None, None
+    try:   # dram bytes per launch of the same kernel from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_contract_ncu.json")) as f:
+            prof = json.load(f)
+        if N == 2000 and d == 12:
+            traffic = prof["traffic_bytes_per_launch"] * (cands_per_launch / (296 * 128))
+            traffic_src = prof["source"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "kernel": "var_contract_kernel (FP64 DMMA.8x8x4)",
                 "flop_per_candidate": flop_per_cand,
                 "ms_per_launch": contract_ms_per_launch,
