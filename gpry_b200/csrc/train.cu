@@ -731,8 +731,9 @@ template <int KIND>
 static void launch_kmat(const TrainBuffers& b, int nth, cudaStream_t s) {
   const int nb32 = b.Np / 32;
   size_t smem = 2 * 32 * (size_t)(b.d + 1) * 8;
-  const size_t nXd = ((size_t)b.N * b.d + 31) / 32 * 32;
-  (void)nXd;
+  if (smem > 48 * 1024)
+    GPRY_CUDA(cudaFuncSetAttribute(kmat_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
   kmat_kernel<KIND><<<dim3(nb32, nb32, nth), 256, smem, s>>>(b.T, b.N, b.d, b.Np, b.cs, b.noise2,
                                                             b.K);
   GPRY_CUDA(cudaGetLastError());

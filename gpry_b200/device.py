@@ -93,6 +93,8 @@ class DeviceGP:
 
     # ------------------------------------------------------------------ candidate side
     def _prep_X(self, X):
+        if self.kind is None:
+            raise _lib.GpryB200Error("no model uploaded into this DeviceGP")
         if _is_torch_cuda(X):
             if X.dtype.is_floating_point and X.element_size() == 8 and X.is_contiguous():
                 return X, int(X.shape[0]), _lib.X_ON_DEVICE
