@@ -436,6 +436,26 @@ def run_ours(args):
                 "stage_ms_per_step": {k: tm[k] / args.steps for k in
                                       ("build_ms", "contract_ms", "finish_ms", "topk_ms")}}
 
+    # ---- every rank checks a sample of ITS OWN shard against the oracle (first / middle / last
+    # tiles), max error reduced over ranks ----
+    shard_err = None
+    if not args.no_cpu_baseline:
+        from oracle import gp_oracle as orc
+        Xp, yp, thp, bp = synthetic_problem(N, d)
+        st_o = orc.GPState("rbf", thp, Xp, yp, bounds=bp)
+        pick = torch.cat([torch.arange(0, 500), torch.arange(M // 2, M // 2 + 500),
+                          torch.arange(M - 500, M)]).to(dev_t)
+        Xs = Xd[pick].contiguous()
+        mg, sg, ag = dev.predict_logexp(Xs, zeta, sig, ymax, stream=stream)
+        mo, so, ao = orc.predict_logexp(st_o, Xs.cpu().numpy())
+        errs = torch.tensor([np.max(np.abs(mg.cpu().numpy() - mo)) / st_o.y_std,
+                             np.max(np.abs(sg.cpu().numpy() ** 2 - so ** 2)) / st_o.y_std ** 2],
+                            dtype=torch.float64, device=dev_t)
+        if world > 1:
+            dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        shard_err = {"n_per_rank": int(len(pick)), "mean_err": float(errs[0]),
+                     "var_err": float(errs[1])}
+
     # ---- agreement check + CPU baseline (rank 0, N = 1 run only for the baseline) ----
     agreement, cpu_baseline = None, None
     if rank == 0 and not args.no_cpu_baseline:
@@ -457,9 +477,12 @@ def run_ours(args):
         a1, i1, _, _, _ = dev.predict_logexp_topk(Xd, zeta, sig, ymax, Kp, stream=stream,
                                                   device_out=True, want_X=False)
         agreement["topk_identical"] = bool(torch.equal(i1, ref_idx[:Kp]))
+        agreement["all_shards"] = shard_err
         agreement["verified"] = bool(agreement["mean_err"] < 1e-10
                                      and agreement["var_err"] < 1e-10
-                                     and agreement["topk_identical"])
+                                     and agreement["topk_identical"]
+                                     and shard_err["mean_err"] < 1e-10
+                                     and shard_err["var_err"] < 1e-10)
         cores, blas = cpu_thread_info()
         if world == 1:
             cpu_baseline = {"value": thr, "unit": UNIT, "cores": cores, "kind": "port",

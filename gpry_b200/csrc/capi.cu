@@ -71,6 +71,56 @@ static const double* stage_in(gpry_state* st, const double* X, size_t n, bool on
   return buf.p;
 }
 
+// Host candidates: enqueue the H2D copy in blocks on a dedicated copy stream and run the
+// pipeline block by block behind the matching event, so that only the first block's copy is
+// exposed.  Device candidates: one call.
+static void run_pipeline_blocks(gpry_state* st, const double* X, int64_t M, bool x_dev,
+                                bool want_var, bool want_acq, double zeta, double sigma_n,
+                                double y_max, double* dm, double* ds, double* da,
+                                const double** dX_out, cudaStream_t s) {
+  const int d = st->d;
+  if (x_dev) {
+    *dX_out = X;
+    predict_pipeline(st, X, M, dm != nullptr, want_var, want_acq, zeta, sigma_n, y_max, dm, ds, da,
+                     s);
+    return;
+  }
+  st->Xdev.reserve((size_t)M * d);
+  *dX_out = st->Xdev.p;
+  const int64_t block = (int64_t)56 * 2 * st->n_sm * TILE_ROWS;   // multiple of the chunk size
+  const int nblocks = (int)((M + block - 1) / block);
+  if (nblocks <= 1) {
+    TimedScope ts(st, s, T_H2D, 0);
+    GPRY_CUDA(cudaMemcpyAsync(st->Xdev.p, X, (size_t)M * d * 8, cudaMemcpyHostToDevice, s));
+  } else {
+    if (!st->copy_stream)
+      GPRY_CUDA(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
+    if (!st->call_start)
+      GPRY_CUDA(cudaEventCreateWithFlags(&st->call_start, cudaEventDisableTiming));
+    while ((int)st->copy_events.size() < nblocks) {
+      cudaEvent_t e;
+      GPRY_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      st->copy_events.push_back(e);
+    }
+    // the staging buffer may still be read by work queued earlier on the compute stream
+    GPRY_CUDA(cudaEventRecord(st->call_start, s));
+    GPRY_CUDA(cudaStreamWaitEvent(st->copy_stream, st->call_start, 0));
+    for (int b = 0; b < nblocks; b++) {
+      const int64_t off = b * block, n = std::min(block, M - off);
+      GPRY_CUDA(cudaMemcpyAsync(st->Xdev.p + off * d, X + off * d, (size_t)n * d * 8,
+                                cudaMemcpyHostToDevice, st->copy_stream));
+      GPRY_CUDA(cudaEventRecord(st->copy_events[b], st->copy_stream));
+    }
+  }
+  for (int b = 0; b < nblocks; b++) {
+    const int64_t off = b * block, n = std::min(block, M - off);
+    if (nblocks > 1) GPRY_CUDA(cudaStreamWaitEvent(s, st->copy_events[b], 0));
+    predict_pipeline(st, st->Xdev.p + off * d, n, dm != nullptr, want_var, want_acq, zeta, sigma_n,
+                     y_max, dm ? dm + off : nullptr, ds ? ds + off : nullptr,
+                     da ? da + off : nullptr, s);
+  }
+}
+
 }  // namespace gpry
 
 using namespace gpry;
@@ -114,6 +164,9 @@ int gpry_state_destroy(gpry_state* st) {
     cudaSetDevice(st->device);
     resolve_timings(st);
     for (auto e : st->pool) cudaEventDestroy(e);
+    for (auto e : st->copy_events) cudaEventDestroy(e);
+    if (st->call_start) cudaEventDestroy(st->call_start);
+    if (st->copy_stream) cudaStreamDestroy(st->copy_stream);
     st->prm_dev.release(); st->T.release(); st->Xt.release(); st->alpha.release();
     st->Vt.release(); st->Ks.release(); st->meanp.release(); st->ssqp.release();
     st->Xdev.release(); st->o_mean.release(); st->o_std.release(); st->o_acq.release();
@@ -177,7 +230,6 @@ static void predict_common(gpry_state* st, const double* X, int64_t M, bool want
   GPRY_CHECK_ARG(X != nullptr, "X is NULL");
   GPRY_CUDA(cudaSetDevice(st->device));
   const bool x_dev = where & GPRY_X_ON_DEVICE, o_dev = where & GPRY_OUT_ON_DEVICE;
-  const double* dX = stage_in(st, X, (size_t)M * st->d, x_dev, st->Xdev, s);
   double *dm = nullptr, *ds = nullptr, *da = nullptr;
   if (want_mean && out_mean) {
     if (o_dev) dm = out_mean; else { st->o_mean.reserve(M); dm = st->o_mean.p; }
@@ -189,8 +241,9 @@ static void predict_common(gpry_state* st, const double* X, int64_t M, bool want
     if (o_dev) da = out_acq; else { st->o_acq.reserve(M); da = st->o_acq.p; }
   }
   const bool need_var = (ds != nullptr) || (da != nullptr);
-  predict_pipeline(st, dX, M, dm != nullptr, need_var, da != nullptr, zeta, sigma_n, y_max, dm, ds,
-                   da, s);
+  const double* dX = nullptr;
+  run_pipeline_blocks(st, X, M, x_dev, need_var, da != nullptr, zeta, sigma_n, y_max, dm, ds, da,
+                      &dX, s);
   if (!o_dev) {
     TimedScope ts(st, s, T_D2H, 0);
     if (dm) GPRY_CUDA(cudaMemcpyAsync(out_mean, dm, M * 8, cudaMemcpyDeviceToHost, s));
@@ -232,12 +285,12 @@ int gpry_predict_logexp_topk(gpry_state* st, const double* X, int64_t M, double 
     GPRY_CUDA(cudaSetDevice(st->device));
     const bool x_dev = where & GPRY_X_ON_DEVICE, o_dev = where & GPRY_OUT_ON_DEVICE;
     const int d = st->d;
-    const double* dX = stage_in(st, X, (size_t)M * d, x_dev, st->Xdev, s);
     st->o_mean.reserve(M);
     st->o_std.reserve(M);
     st->o_acq.reserve(M);
-    predict_pipeline(st, dX, M, true, true, true, zeta, sigma_n, y_max, st->o_mean.p, st->o_std.p,
-                     st->o_acq.p, s);
+    const double* dX = nullptr;
+    run_pipeline_blocks(st, X, M, x_dev, true, true, zeta, sigma_n, y_max, st->o_mean.p,
+                        st->o_std.p, st->o_acq.p, &dX, s);
     double* d_keys;
     int64_t* d_idx;
     int64_t n = topk_device(st, st->o_acq.p, M, Kp, idx_offset, &d_keys, &d_idx, s);

@@ -95,6 +95,11 @@ struct gpry_state {
   int f_N = 0, f_d = 0, f_kind = -1;
   bool f_valid = false;
 
+  // host-input pipelining: H2D copies of later blocks overlap the compute of earlier ones
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
+  cudaEvent_t call_start = nullptr;
+
   // profiling
   bool profiling = false;
   std::vector<gpry::EventPair> pending;
