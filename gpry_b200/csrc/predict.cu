@@ -99,7 +99,7 @@ kstar_build_kernel(const double* __restrict__ X, int64_t M, int d, int64_t cand0
 #pragma unroll
     for (int jj = 0; jj < 4; jj++) {
       const double2* tp = reinterpret_cast<const double2*>(Ts + (size_t)(j4 + jj) * DP);
-      double r2 = 0.0;
+      double r2 = 0.0;      // summed in index order, as cdist does (sklearn:kernels.py:1569)
 #pragma unroll
       for (int k2 = 0; k2 < DP / 2; k2++) {
         double2 t = tp[k2];
