@@ -171,6 +171,51 @@ def fit_case(gpry):
           "n_eval_loglike", gpr.n_eval_loglike)
 
 
+def loop_case(gpry):
+    """BASELINE config #1 in miniature (examples/readme_example.py): an active-learning loop
+    on a 2-D curved log-likelihood with the reference's own pieces -- predict, LogExp.f,
+    RankedPool(method="single sort acq"), append_to_data -- at fixed hyper-parameters, with the
+    MC sample replaced by seeded uniform draws (NORA's test sampler).  Stores the sequence of
+    acquired points: given identical MC samples the acquisitions must be identical."""
+    from functools import partial
+    import warnings
+    d, n_points, n_iter, n_mc = 2, 2, 5, 3000
+    bounds = np.array([[-4.0, 4.0], [-2.0, 6.0]])
+
+    def loglike(X):   # curved ("banana") Gaussian
+        return -0.5 * (X[:, 0] ** 2 / 1.5 + (X[:, 1] - 0.5 * X[:, 0] ** 2) ** 2 / 0.5)
+
+    rng = np.random.default_rng(2024)
+    X0 = rng.uniform(bounds[:, 0], bounds[:, 1], size=(12, d))
+    theta = np.log([25.0, 0.25, 0.2])
+    gpr = make_reference_gpr(gpry, "rbf", X0, loglike(X0), theta, bounds, noise_level=1e-2)
+    LogExp = gpry.acquisition_functions.LogExp
+    zeta = d ** (-0.85)
+    acquired, y_lies, acqs = [], [], []
+    for it in range(n_iter):
+        X_mc = rng.uniform(bounds[:, 0], bounds[:, 1], size=(n_mc, d))
+        y_mc, s_mc = gpr.predict(X_mc, return_std=True, validate=False)
+        acq_func = partial(LogExp.f, baseline=gpr.y_max, noise_level=gpr.noise_level, zeta=zeta)
+        with np.errstate(divide="ignore"):
+            a_mc = acq_func(y_mc, s_mc)
+            pool = gpry.gp_acquisition.RankedPool(n_points, gpr=gpr, acq_func=acq_func, verbose=0)
+            pool.add(X_mc, y_mc, s_mc, a_mc, method="single sort acq")
+            pool = pool.copy(drop_empty=True)
+            X_new, y_lie = pool.X[:n_points].copy(), pool.y[:n_points].copy()
+            acq_new = acq_func(y_lie, pool.sigma[:n_points])
+        acquired.append(X_new), y_lies.append(y_lie), acqs.append(acq_new)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gpr.append_to_data(X_new, loglike(X_new), fit_gpr=False)
+    Xc = rng.uniform(bounds[:, 0], bounds[:, 1], size=(64, d))
+    mean, std = gpr.predict(Xc, return_std=True, validate=False)
+    np.savez_compressed(os.path.join(OUT, "loop_banana_d2.npz"), bounds=bounds, X0=X0, theta=theta,
+                        seed=2024, n_points=n_points, n_iter=n_iter, n_mc=n_mc, zeta=zeta,
+                        acquired=np.array(acquired), y_lies=np.array(y_lies),
+                        acqs=np.array(acqs), Xc=Xc, mean=mean, std=std, n_train=gpr.n)
+    print("loop_banana_d2: acquired", np.array(acquired).shape, "final N", gpr.n)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gpry = import_reference()
@@ -185,6 +230,7 @@ def main():
          store_train=False)
     nonpd_case(gpry)
     fit_case(gpry)
+    loop_case(gpry)
 
 
 if __name__ == "__main__":

@@ -217,3 +217,56 @@ def test_fit_like_reference():
         assert gpr.log_marginal_likelihood_value_ >= ref - 1e-3 * abs(ref)
         mean = gpr.predict(z["X_train"][:5])
         assert np.allclose(mean, z["y_train"][:5], atol=1e-2 * np.std(z["y_train"]))
+
+
+def test_active_learning_loop_like_reference():
+    """BASELINE config #1 in miniature: given identical MC samples, the acquisitions of an
+    active-learning loop (predict -> LogExp -> ranked pool with KB -> append) are identical to
+    the reference's, iteration after iteration (golden trace: oracle/gen_golden.py:loop_case)."""
+    from gpry_b200.acquisition_functions import LogExp
+    from gpry_b200.gp_acquisition import NORA
+    from gpry_b200.gpr import GaussianProcessRegressor
+    from gpry_b200.preprocessing import Normalize_bounds, Normalize_y
+    z = np.load(os.path.join(GOLDEN_DIR, "loop_banana_d2.npz"))
+    bounds = z["bounds"]
+    d = bounds.shape[0]
+
+    def loglike(X):
+        return -0.5 * (X[:, 0] ** 2 / 1.5 + (X[:, 1] - 0.5 * X[:, 0] ** 2) ** 2 / 0.5)
+
+    rng = np.random.default_rng(int(z["seed"]))
+    X0 = rng.uniform(bounds[:, 0], bounds[:, 1], size=(12, d))
+    assert np.array_equal(X0, z["X0"])
+    gpr = GaussianProcessRegressor(kernel="RBF", bounds=bounds, noise_level=1e-2,
+                                   preprocessing_X=Normalize_bounds(bounds),
+                                   preprocessing_y=Normalize_y(), account_for_inf=None, verbose=0)
+    gpr.kernel_ = deepcopy(gpr.kernel)
+    gpr.kernel_.theta = z["theta"]
+    gpr.append_to_data(X0, loglike(X0), fit_gpr=False)
+    nora = NORA(bounds, acq_func=LogExp(zeta=float(z["zeta"])), kprime=64)
+    n_points = int(z["n_points"])
+    for it in range(int(z["n_iter"])):
+        X_mc = rng.uniform(bounds[:, 0], bounds[:, 1], size=(int(z["n_mc"]), d))
+        X_new, y_lie, acq = nora.multi_add(gpr, n_points=n_points, X_mc=X_mc)
+        assert np.array_equal(X_new, z["acquired"][it]), f"iteration {it}"
+        assert scaled_err(y_lie, z["y_lies"][it], 1.0) < 1e-9
+        assert scaled_err(acq, z["acqs"][it], 1.0) < 1e-8
+        gpr.append_to_data(X_new, loglike(X_new), fit_gpr=False)
+    assert gpr.n == int(z["n_train"])
+    Xc = rng.uniform(bounds[:, 0], bounds[:, 1], size=(64, d))
+    assert np.array_equal(Xc, z["Xc"])
+    mean, std = gpr.predict(Xc, return_std=True)
+    sy = gpr.preprocessing_y.std_
+    assert scaled_err(mean, z["mean"], sy) < 1e-9
+    assert scaled_err(std ** 2, z["std"] ** 2, sy ** 2) < 1e-9
+
+
+def test_readme_example_runs():
+    import importlib.util
+    path = os.path.join(os.path.dirname(GOLDEN_DIR), "..", "examples", "readme_example.py")
+    spec = importlib.util.spec_from_file_location("readme_example", os.path.abspath(path))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gpr, err = mod.main(n_iter=6, n_points=2, seed=3)
+    assert gpr.n == 8 + 12 and gpr.fitted
+    assert np.median(err) < 0.5          # the surrogate tracks the log-posterior where it matters
