@@ -310,86 +310,85 @@ class GaussianProcessRegressor:
         difference_to_nth_point = y_sorted[-1] - y_sorted[-min(n, len(y_sorted))]
         return max(reference_diff_threshold, difference_to_nth_point + epsilon)
 
-    def append_to_data(self, X, y, noise_level=None, fit_gpr=True, fit_classifier=True):
-        """gpr.py:577-753 (same control flow; the two numeric calls at the end run on the
-        GPU)."""
-        fit_preprocessors = False
-        fit_gpr_kwargs = None
+    @staticmethod
+    def _fit_request(fit_gpr, fit_classifier):
+        """Normalises the ``fit_gpr`` argument (gpr.py:648-668) -> (kwargs or None, refit
+        classifier?).  A hyper-parameter fit implies a classifier (and pre-processor) refit."""
+        if fit_gpr is False:
+            return None, bool(fit_classifier)
         if fit_gpr is True:
-            fit_classifier = True
-            fit_gpr_kwargs = {}
-        elif str(fit_gpr) == "simple":
-            fit_classifier = True
-            fit_gpr_kwargs = {"simple": True}
-            fit_gpr = True
-        elif isinstance(fit_gpr, dict):
-            fit_classifier = True
-            fit_gpr_kwargs = deepcopy(fit_gpr)
-            fit_gpr = True
-        elif fit_gpr is not False:
-            raise ValueError("`fit_gpr` needs to be bool, 'simple', or a dict of args for the "
-                             f"`fit_gpr_hyperparameters` method. Got {fit_gpr}.")
-        if fit_classifier:
-            fit_preprocessors = True
-        force_fit_gpr = False
-        if X is None and y is None:
-            X, y = np.empty((0, self.d)), np.empty((0,))
-            force_fit_gpr = fit_gpr
+            return {}, True
+        if isinstance(fit_gpr, str) and fit_gpr == "simple":
+            return {"simple": True}, True
+        if isinstance(fit_gpr, dict):
+            return deepcopy(fit_gpr), True
+        raise ValueError("`fit_gpr` needs to be bool, 'simple', or a dict of args for the "
+                         f"`fit_gpr_hyperparameters` method. Got {fit_gpr}.")
+
+    def _finite_mask(self):
+        """Which of all points added so far enter the GPR (gpr.py:689-704); the rest is left
+        to the infinities classifier.  Returns (mask, threshold used or None)."""
+        if self.infinities_classifier is None:
+            return np.ones(len(self.y_train_all), dtype=bool), None
+        threshold = self._diff_threshold_if_keep_n_finite(
+            self.y_train_all, self.keep_min_finite, self._diff_threshold)
+        return self.infinities_classifier._is_finite_raw(self.y_train_all, threshold), threshold
+
+    def append_to_data(self, X, y, noise_level=None, fit_gpr=True, fit_classifier=True):
+        """Adds points and updates the model: gpr.py:577-753.  ``fit_gpr``: True / dict /
+        'simple' re-fit the hyper-parameters (GPU: batched LML + gradient), False keeps them
+        and only re-factorises (GPU: Cholesky, L^-1, alpha).  ``X = y = None`` re-fits without
+        new points.  Host-side bookkeeping is as in the reference."""
+        fit_kwargs, refit_classifier = self._fit_request(fit_gpr, fit_classifier)
+        refit_only = X is None and y is None
+        if refit_only:
             if noise_level is not None:
                 raise ValueError("Cannot give a noise level if X and y are not given.")
+            X, y = np.empty((0, self.d)), np.empty((0,))
         elif X is None or y is None:
             raise ValueError("If passing X, y needs to be passed too, and viceversa.")
         X = np.atleast_2d(np.asarray(X, dtype=float))
         y = np.atleast_1d(np.asarray(y, dtype=float))
-        noise_level_valid = self._validate_noise_level(noise_level, len(y))
+        new_noise = self._validate_noise_level(noise_level, len(y))
+        # 1. raw bookkeeping
         self.n_last_appended = len(y)
         self.X_train_all = np.append(self.X_train_all, X, axis=0)
         self.y_train_all = np.append(self.y_train_all, y)
-        self._update_noise_level(noise_level_valid)
-        if self.infinities_classifier is None:
-            is_finite_all = np.full(fill_value=True, shape=(len(self.y_train_all),))
-            X_finite = np.copy(self.X_train_all)
-            y_finite = np.copy(self.y_train_all)
-        else:
-            diff_threshold_keep_n = self._diff_threshold_if_keep_n_finite(
-                self.y_train_all, self.keep_min_finite, self._diff_threshold)
-            is_finite_all = self.infinities_classifier._is_finite_raw(
-                self.y_train_all, diff_threshold_keep_n)
-            X_finite = np.copy(self.X_train_all[is_finite_all])
-            y_finite = np.copy(self.y_train_all[is_finite_all])
-        if fit_preprocessors:
-            self.preprocessing_X.fit(X_finite, y_finite)
-            self.preprocessing_y.fit(X_finite, y_finite)
+        self._update_noise_level(new_noise)
+        # 2. finite selection, pre-processors (refit together with the classifier), transforms
+        finite, threshold = self._finite_mask()
+        if refit_classifier:
+            self.preprocessing_X.fit(self.X_train_all[finite], self.y_train_all[finite])
+            self.preprocessing_y.fit(self.X_train_all[finite], self.y_train_all[finite])
         self.X_train_all_ = self.preprocessing_X.transform(self.X_train_all)
         self.y_train_all_ = self.preprocessing_y.transform(self.y_train_all)
-        noise_level_array = (
-            np.full(fill_value=self.noise_level, shape=(len(self.y_train_all_),))
-            if isinstance(self.noise_level, Number) else self.noise_level)
-        self.noise_level_ = self.preprocessing_y.transform_scale(noise_level_array)
+        noise_all = (np.full(len(self.y_train_all_), self.noise_level)
+                     if isinstance(self.noise_level, Number) else self.noise_level)
+        self.noise_level_ = self.preprocessing_y.transform_scale(noise_all)
+        # 3. classifier (lives in the transformed space: gets all points every time)
+        if self.infinities_classifier is not None and refit_classifier:
+            predicted = self.infinities_classifier.fit(
+                self.X_train_all_, self.y_train_all_,
+                self.preprocessing_y.transform_scale(threshold))
+            assert np.array_equal(finite, predicted), \
+                "Infinities classifier miss-classified at least 1 point."
+        n_new = self.n_last_appended
         if self.infinities_classifier is None:
-            is_finite_last_appended = np.full(fill_value=True, shape=(self.n_last_appended,))
-        else:
-            if fit_classifier:
-                diff_threshold_keep_n_ = self.preprocessing_y.transform_scale(
-                    diff_threshold_keep_n)
-                is_finite_predict = self.infinities_classifier.fit(
-                    self.X_train_all_, self.y_train_all_, diff_threshold_keep_n_)
-                assert np.array_equal(is_finite_all, is_finite_predict), \
-                    "Infinities classifier miss-classified at least 1 point."
-            is_finite_last_appended = is_finite_all[-self.n_last_appended:] \
-                if self.n_last_appended else is_finite_all[:0]
-        self.n_last_appended_finite = int(sum(is_finite_last_appended))
-        if not self.n_last_appended_finite and not force_fit_gpr:
-            return self
-        self.X_train = X_finite
-        self.y_train = y_finite
+            self.n_last_appended_finite = n_new
+        else:   # NB: the reference slices [-n_new:], i.e. ALL points when n_new == 0 (:735-737)
+            self.n_last_appended_finite = int(np.sum(finite[-n_new:]))
+        if not self.n_last_appended_finite and not (refit_only and fit_kwargs is not None):
+            return self        # nothing new for the GPR (gpr.py:738-741)
+        # 4. GPR training set in both spaces, then the device work
+        self.X_train = np.copy(self.X_train_all[finite])
+        self.y_train = np.copy(self.y_train_all[finite])
         self.X_train_ = self.preprocessing_X.transform(self.X_train)
         self.y_train_ = self.preprocessing_y.transform(self.y_train)
-        self.alpha = self.noise_level_[is_finite_all] ** 2
+        self.alpha = self.noise_level_[finite] ** 2       # NB: not alpha_ (gpr.py:747)
         self.newly_appended_for_inv = self.n_last_appended_finite
         self._dev_dirty = True
-        if fit_gpr:
-            self.fit_gpr_hyperparameters(**fit_gpr_kwargs)
+        if fit_kwargs is not None:
+            self.fit_gpr_hyperparameters(**fit_kwargs)
         else:
             self._update_model()
         self.update_trust_region()
