@@ -270,3 +270,66 @@ def test_readme_example_runs():
     gpr, err = mod.main(n_iter=6, n_points=2, seed=3)
     assert gpr.n == 8 + 12 and gpr.fitted
     assert np.median(err) < 0.5          # the surrogate tracks the log-posterior where it matters
+
+
+class ThresholdClassifier:
+    """Minimal stand-in with the interface of gpry.svm.SVM (svm.py:308-347): points with
+    transformed x_0 > 0.9 are predicted 'infinite'; y below max - threshold is 'infinite'."""
+
+    def __init__(self):
+        self.n = 0
+        self.y_finite = None
+
+    def _is_finite_raw(self, y, diff_threshold):
+        return y > np.max(y) - diff_threshold
+
+    def fit(self, X_, y_, diff_threshold_):
+        self.n = len(y_)
+        self.y_finite = y_ > np.max(y_) - diff_threshold_
+        return self.y_finite
+
+    def is_finite(self, y_):
+        return np.ones(len(y_), dtype=bool)
+
+    def predict(self, X_, validate=True):
+        return X_[:, 0] <= 0.9
+
+
+def test_classifier_and_trust_region_masks():
+    """gpr.py:1104-1109, 1136-1174, 1196-1201, 1229-1231: rows the classifier calls infinite get
+    mean = minus_inf_value and std = 0; rows outside the trust region get mean = -inf but keep
+    their std; predict_std ignores the trust region."""
+    from gpry_b200.gpr import GaussianProcessRegressor
+    from gpry_b200.preprocessing import Normalize_bounds, Normalize_y
+    g = load_golden("rbf_d8_n300")
+    plain = make_gpr(g)
+    gpr = GaussianProcessRegressor(
+        kernel="RBF", bounds=g["bounds"], noise_level=g["noise_level"],
+        preprocessing_X=Normalize_bounds(g["bounds"]), preprocessing_y=Normalize_y(),
+        account_for_inf=ThresholdClassifier(), inf_threshold=1e9, verbose=0,
+        trust_region_factor=1.0)
+    gpr.kernel_ = deepcopy(gpr.kernel)
+    gpr.kernel_.theta = g["theta"]
+    gpr.append_to_data(g["X_train"], g["y_train"], fit_gpr=False)
+    assert gpr.n == g["N"] and gpr.n_total == g["N"]
+    Xc = g["Xc"].copy()
+    Xc[:5] = g["bounds"][:, 0] - 1.0            # outside the trust region (and the prior box)
+    ref_m, ref_s = plain.predict(Xc, return_std=True)
+    m, s = gpr.predict(Xc, return_std=True)
+    X_ = gpr.preprocessing_X.transform(Xc)
+    inf_rows = X_[:, 0] > 0.9
+    out_trust = ~np.all((Xc >= gpr.trust_bounds[:, 0]) & (Xc <= gpr.trust_bounds[:, 1]), axis=1)
+    assert inf_rows.any() and out_trust[:5].all()
+    assert np.all(m[inf_rows | out_trust] == -np.inf)
+    assert np.all(s[inf_rows] == 0.0)
+    ok = ~(inf_rows | out_trust)
+    assert np.array_equal(m[ok], ref_m[ok]) and np.array_equal(s[~inf_rows], ref_s[~inf_rows])
+    s_only = gpr.predict_std(Xc)
+    assert np.array_equal(s_only[~inf_rows], ref_s[~inf_rows]) and np.all(s_only[inf_rows] == 0)
+    m2 = gpr.predict(Xc, ignore_trust_region=True)
+    assert np.array_equal(m2[~inf_rows], ref_m[~inf_rows])
+    gpr.minus_inf_value = -1e300                # read at call time (UltraNest path, :788-792)
+    assert np.all(gpr.predict(Xc)[inf_rows] == -1e300)
+    all_inf = np.tile(g["bounds"][:, 1], (3, 1))        # x_0 = 1 > 0.9 for every row
+    m3, s3 = gpr.predict(all_inf, return_std=True)
+    assert np.all(m3 == -1e300) and np.all(s3 == 0)
