@@ -527,7 +527,13 @@ class GaussianProcessRegressor:
         def flush_locked():
             idx = sorted(pending)
             thetas = np.array([pending[i] for i in idx])
-            lml, grad = self.log_marginal_likelihood_batch(thetas, eval_gradient=True)
+            try:
+                lml, grad = self.log_marginal_likelihood_batch(thetas, eval_gradient=True)
+            except Exception as excpt:     # wake everybody up: nobody must wait forever
+                errors.append(excpt)
+                pending.clear()
+                cond.notify_all()
+                raise
             for j, i in enumerate(idx):
                 results[i] = (-lml[j], -grad[j])
             pending.clear()
@@ -536,11 +542,15 @@ class GaussianProcessRegressor:
         def obj(i):
             def f(theta):
                 with cond:
+                    if errors:
+                        raise RuntimeError("another restart failed") from errors[0]
                     pending[i] = np.array(theta, dtype=float)
                     if len(pending) == len(active):
                         flush_locked()
                     else:
                         while i not in results:
+                            if errors:
+                                raise RuntimeError("another restart failed") from errors[0]
                             cond.wait()
                     return results.pop(i)
             return f
@@ -552,13 +562,19 @@ class GaussianProcessRegressor:
                     res = scipy.optimize.minimize(obj(i), theta_initials[i], method="L-BFGS-B",
                                                   jac=True, bounds=bounds)
                 optima[i] = (res.x, res.fun)
-            except Exception as excpt:  # pragma: no cover
-                errors.append(excpt)
+            except Exception as excpt:
+                with cond:
+                    if not errors:
+                        errors.append(excpt)
             finally:
                 with cond:
                     active.discard(i)
-                    if pending and len(pending) == len(active):
-                        flush_locked()
+                    if pending and len(pending) == len(active) and not errors:
+                        try:
+                            flush_locked()
+                        except Exception:
+                            pass
+                    cond.notify_all()
 
         threads = [threading.Thread(target=run, args=(i,)) for i in range(n)]
         for t in threads:

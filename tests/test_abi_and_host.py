@@ -154,3 +154,37 @@ def test_gpr_host_logic_without_gpu():
     g2 = pickle.loads(pickle.dumps(gpr))
     assert g2._dev is None and g2.d == 4
     assert deepcopy(gpr).kernel == gpr.kernel
+
+
+def test_lockstep_restart_driver_without_gpu():
+    """The lock-step multi-restart driver (one batched objective call per round) reaches the
+    optima a serial L-BFGS-B reaches, and propagates a failing evaluation instead of hanging."""
+    import scipy.optimize
+    from gpry_b200.gpr import GaussianProcessRegressor
+    bounds = np.array([[0.0, 1.0]] * 2)
+    g = GaussianProcessRegressor(kernel="RBF", bounds=bounds, verbose=0)
+    target, w = np.array([1.0, -1.0, 0.5]), np.array([1.0, 2.0, 3.0])
+    batch_sizes = []
+
+    def fake_batch(thetas, eval_gradient=True):
+        thetas = np.atleast_2d(thetas)
+        batch_sizes.append(len(thetas))
+        return -np.sum(w * (thetas - target) ** 2, axis=1), -2 * w * (thetas - target)
+
+    g.log_marginal_likelihood_batch = fake_batch
+    box = np.array([[-5.0, 5.0]] * 3)
+    starts = [np.zeros(3), np.full(3, 3.0), np.array([-4.0, 2.0, 1.0]), np.array([4.0, -4.0, 4.0])]
+    optima = g._lockstep_optimization(starts, box)
+    for th0, (x, f) in zip(starts, optima):
+        ref = scipy.optimize.minimize(lambda t: (np.sum(w * (t - target) ** 2),
+                                                 2 * w * (t - target)),
+                                      th0, method="L-BFGS-B", jac=True, bounds=box)
+        assert np.allclose(x, ref.x, atol=1e-12) and f == pytest.approx(ref.fun, abs=1e-15)
+    assert max(batch_sizes) == 4 and len(batch_sizes) < 4 * 12
+
+    def boom(thetas, eval_gradient=True):
+        raise ValueError("device failure")
+
+    g.log_marginal_likelihood_batch = boom
+    with pytest.raises(ValueError):
+        g._lockstep_optimization(starts, box)
