@@ -342,8 +342,11 @@ __device__ __forceinline__ void cp_async_wait() {
 
 
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
+  // grid = (batch, row tiles, column tiles): the batch index varies fastest in the dispatch
+  // order, so the tiles of all thetas are issued longest-K-first (row tile 0 of every theta,
+  // then row tile 1, ...), which balances the triangular k ranges across the SMs.
   int mt = blockIdx.y;
-  const int nt = blockIdx.x;
+  const int nt = blockIdx.z;
   const int si = (mt >= g.seg[0].m_tiles) ? 1 : 0;
   if (si) mt -= g.seg[0].m_tiles;
   const GemmSeg& sg = g.seg[si];
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
   const int m0 = mt * TILE_ROWS, n0 = nt * TILE_ROWS;
   const int k_lo = sg.klo_row ? m0 : 0;
   const int nk = (g.K - k_lo) / TILE_K;
-  const size_t bz = blockIdx.z;
+  const size_t bz = blockIdx.x;
 
   const double* Ag = sg.A + bz * sg.sA + (size_t)m0 * sg.lda + k_lo;
   const double* Bg = g.B + bz * g.sB + (size_t)n0 * g.ldb + k_lo;
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
 static void launch_gemm(const GemmArgs& g, int batch, cudaStream_t s) {
   const int mt = g.seg[0].m_tiles + g.seg[1].m_tiles;
   if (mt <= 0 || g.n_tiles <= 0 || g.K <= 0 || batch <= 0) return;
-  dim3 grid(g.n_tiles, mt, batch);
+  dim3 grid(batch, mt, g.n_tiles);
   gemm_nt_kernel<<<grid, G_THREADS, sizeof(GemmSmem), s>>>(g);
   GPRY_CUDA(cudaGetLastError());
 }
@@ -564,7 +567,7 @@ lml_grad_kernel(const double* __restrict__ X, const double* __restrict__ Tall, i
   double* Xj = Xi + 32 * (d + 1);       // [32][d+1]
   double* Ti = Xj + 32 * (d + 1);       // [32][d+1]  X / ell
   double* Tj = Ti + 32 * (d + 1);       // [32][d+1]
-  double* l2 = Tj + 32 * (d + 1);       // [d]  ell^2 (divided by, as the reference does)
+  double* l2 = Tj + 32 * (d + 1);       // [d]  1 / ell^2
   double* red = l2 + d;                 // [8 warps][P]
   const int tid = threadIdx.x;
   if (bj > bi) {
@@ -579,7 +582,7 @@ lml_grad_kernel(const double* __restrict__ X, const double* __restrict__ Tall, i
     Ti[r * (d + 1) + k] = gi < N ? T[(size_t)gi * d + k] : 0.0;
     Tj[r * (d + 1) + k] = gj < N ? T[(size_t)gj * d + k] : 0.0;
   }
-  for (int k = tid; k < d; k += 256) l2[k] = ell[k] * ell[k];   // length_scale**2
+  for (int k = tid; k < d; k += 256) l2[k] = 1.0 / (ell[k] * ell[k]);   // 1 / length_scale**2
   __syncthreads();
   const int tx = tid & 31, ty = tid >> 5, lane = tx, warp = ty;
   // each thread: column tx, rows ty + 8 q.  Pass 1 computes w * (kernel factor) per pair and
@@ -601,7 +604,7 @@ lml_grad_kernel(const double* __restrict__ X, const double* __restrict__ Tall, i
         double sumD = 0.0, r2 = 0.0;
         for (int k = 0; k < d; k++) {
           double df = Xi[rr * (d + 1) + k] - Xj[tx * (d + 1) + k];
-          double D = df * df / l2[k];             // (xi - xj)**2 / length_scale**2
+          double D = df * df * l2[k];             // (xi - xj)**2 / length_scale**2
           sumD += D;
           double a = Ti[rr * (d + 1) + k] - Tj[tx * (d + 1) + k];
           r2 = fma(a, a, r2);                     // pdist(X / l): the value entering K itself
@@ -634,7 +637,7 @@ lml_grad_kernel(const double* __restrict__ X, const double* __restrict__ Tall, i
     for (int q = 0; q < 4; q++) {
       const int rr = ty + 8 * q;
       double df = Xi[rr * (d + 1) + k] - Xj[tx * (d + 1) + k];
-      s = fma(wk[q], df * df / l2[k], s);
+      s = fma(wk[q], df * df * l2[k], s);
     }
     block_sum_to(s, 1 + k);
   }

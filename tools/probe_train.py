@@ -15,8 +15,12 @@ for N, d, B in cfgs:
     noise2 = np.full(N, (1e-2 / y_std) ** 2)
     rng = np.random.default_rng(7)
     thetas = theta + 0.1 * rng.standard_normal((B, d + 1))
-    dev.lml_batched("rbf", X_, noise2, y_, thetas[:1])
-    t0 = time.perf_counter(); lml, grad, info = dev.lml_batched("rbf", X_, noise2, y_, thetas); t1 = time.perf_counter()
+    dev.lml_batched("rbf", X_, noise2, y_, thetas)
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter(); lml, grad, info = dev.lml_batched("rbf", X_, noise2, y_, thetas); t1 = time.perf_counter()
+        best = min(best, t1 - t0)
+    t0, t1 = 0.0, best
     t2 = time.perf_counter(); dev.factorize("rbf", X_, noise2, y_, theta, want_L=False, want_V=False); t3 = time.perf_counter()
     t4 = time.perf_counter(); dev.factorize("rbf", X_, noise2, y_, theta); t5 = time.perf_counter()
     out = dict(N=N, d=d, lml_grad_ms_per_eval=(t1 - t0) / B * 1e3, factorize_device_ms=(t3 - t2) * 1e3,
