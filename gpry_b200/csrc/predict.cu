@@ -352,7 +352,9 @@ var_contract_kernel(const double* __restrict__ Vt, const double* __restrict__ Ks
         }
         __syncwarp();
         if (lane == 0) {
+          __threadfence_block();   // release: this warp's reads of the slot are done
           if (atomicAdd(&sm.released[stage], 1) == VC_WARPS - 1) {   // last warp out refills
+            __threadfence_block();   // acquire: every warp's release is visible
             sm.released[stage] = 0;
             if (nseq.valid(n_tiles)) issue(nseq, stage);
           }

@@ -1,0 +1,31 @@
+"""Small end-to-end pass over every C-ABI entry point, for compute-sanitizer
+(memcheck / racecheck / initcheck):  compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+import sys
+import numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+from oracle import gp_oracle as orc
+from gpry_b200 import DeviceGP
+from test_gpu_predict import upload_from_oracle
+
+dev = DeviceGP(0)
+for kind, N, d, M in [("rbf", 300, 5, 700), ("matern25", 140, 33, 130)]:
+    X, y, theta, bounds = orc.synthetic_problem(N, d)
+    st = orc.GPState(kind, theta, X, y, bounds=bounds)
+    upload_from_oracle(dev, st)
+    Xc = np.random.default_rng(0).uniform(size=(M, d))
+    m, s = dev.predict(Xc, return_std=True)
+    m2, _ = dev.predict(Xc)
+    a, idx, mm, ss, Xo = dev.predict_logexp_topk(Xc, 0.3, st.noise_level, st.y_max, 64)
+    g = dev.mean_grad(Xc[0]); gs, sd = dev.std_grad(Xc[0])
+    S = dev.posterior_cov(Xc[:200])
+    K = dev.kernel_cross(kind, theta, st.X_train_[:40], st.X_train_[:50])
+    G = dev.kernel_gradient_x(st.X_train_[3])
+    L, V, al, ld, info = dev.factorize(kind, st.X_train_, st.noise2, st.y_train_, theta, keep_on_device=True)
+    c, ell = orc.split_theta(theta)
+    dev.adopt_factorization(c, ell, bounds[:, 0], bounds[:, 1] - bounds[:, 0], st.y_mean, st.y_std, np.inf)
+    m3, s3 = dev.predict(Xc, return_std=True)
+    lml, grad, inf = dev.lml_batched(kind, st.X_train_, st.noise2, st.y_train_, np.array([theta, theta + 0.1, theta - 0.1]))
+    mo, so = orc.predict(st, Xc, return_std=True)
+    print(kind, N, d, "mean err", np.abs(m - mo).max(), "var err", np.abs(s**2 - so**2).max(), "lml", lml, "info", info, inf)
+dev.close()
+print("done")
