@@ -122,6 +122,16 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                : "d"(a), "d"(b));
 }
 
+// shared-memory counter increment with acquire-release semantics at CTA scope
+__device__ __forceinline__ int atom_add_acq_rel_shared(int* p, int v) {
+  int old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], %2;"
+               : "=r"(old)
+               : "r"(smem_u32(p)), "r"(v)
+               : "memory");
+  return old;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -17,7 +17,9 @@
 //                 block-lower-triangular GEMM on FP64 tensor cores (mma.sync m8n8k4 ->
 //                 DMMA.8x8x4), operands streamed by TMA bulk copies through a 6-stage
 //                 mbarrier ring, squared-row-sum epilogue kept in registers.  (DMMA bound)
-//   finish        var = c - ssq, clamp, sqrt, de-normalise, clip, LogExp.
+//   finish        var = c - ssq, clamp, sqrt, de-normalise, clip, LogExp: fused into the
+//                 tile epilogue of var_contract (a separate small kernel only when the row
+//                 blocks of V are split over several CTAs for small pools, or mean only).
 #include <math.h>
 
 #include "state.cuh"
@@ -171,6 +173,44 @@ kstar_build_generic_kernel(const double* __restrict__ X, int64_t M, int d, int D
 }
 
 // ---------------------------------------------------------------------------------------
+// finishing arithmetic (gpr.py:1180-1195, 1207-1227; LogExp.f acquisition_functions.py:
+// 1071-1074), shared by the fused epilogue of var_contract and by finish_kernel
+// ---------------------------------------------------------------------------------------
+struct FinishParams {
+  const double* meanp;   // [JS][chunk_cands] partial means
+  int JS;
+  int chunk_cands;
+  int n_valid;           // candidates of this chunk that exist (the last tile may be ragged)
+  double c, y_mean, y_std, clip_hi;
+  int want_acq;
+  double two_zeta, sigma_n2, y_max;
+  double* o_mean;        // outputs, already offset to the chunk; any may be NULL
+  double* o_std;
+  double* o_acq;
+};
+
+__device__ __forceinline__ void finish_one(const FinishParams& f, int i, bool have_var,
+                                           double ssq) {
+  double m_ = 0.0;
+  for (int s = 0; s < f.JS; s++) m_ += f.meanp[(size_t)s * f.chunk_cands + i];
+  double mean = m_ * f.y_std + f.y_mean;          // preprocessing.py:620
+  mean = fmin(mean, f.clip_hi);                   // gpr.py:1187-1195 (np.clip upper)
+  if (isnan(m_)) mean = m_;
+  if (f.o_mean) f.o_mean[i] = mean;
+  if (have_var) {
+    double var = f.c - ssq;                       // gpr.py:1207-1208
+    if (var < 0.0) var = 0.0;                     // :1214-1219
+    double sd = sqrt(var) * f.y_std;              // :1220, preprocessing.py:630
+    if (f.o_std) f.o_std[i] = sd;
+    if (f.want_acq && f.o_acq) {
+      double v = sd * sd - f.sigma_n2;            // std**2 - noise_level**2
+      v = v > 0.0 ? v : 0.0;                      // np.clip(., 0, None)
+      f.o_acq[i] = f.two_zeta * (mean - f.y_max) + log(sqrt(v));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // var_contract
 // ---------------------------------------------------------------------------------------
 constexpr int VC_STAGES = 6;
@@ -261,7 +301,7 @@ __device__ __forceinline__ void vc_stage(double (&acc)[8][4][2], const double* _
 __global__ void __launch_bounds__(VC_THREADS, 1)
 var_contract_kernel(const double* __restrict__ Vt, const double* __restrict__ Ks, int n_tiles,
                     int N, int nJ, int nKT, int row_splits, double* __restrict__ ssqp,
-                    int chunk_cands) {
+                    int chunk_cands, int fused, FinishParams fin) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VcSmem& sm = *reinterpret_cast<VcSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -352,9 +392,9 @@ var_contract_kernel(const double* __restrict__ Vt, const double* __restrict__ Ks
         }
         __syncwarp();
         if (lane == 0) {
-          __threadfence_block();   // release: this warp's reads of the slot are done
-          if (atomicAdd(&sm.released[stage], 1) == VC_WARPS - 1) {   // last warp out refills
-            __threadfence_block();   // acquire: every warp's release is visible
+          // release (this warp's reads of the slot are done) / acquire (the last warp out sees
+          // every other warp's release) on the slot counter; the last warp out refills
+          if (atom_add_acq_rel_shared(&sm.released[stage], 1) == VC_WARPS - 1) {
             sm.released[stage] = 0;
             if (nseq.valid(n_tiles)) issue(nseq, stage);
           }
@@ -387,9 +427,15 @@ var_contract_kernel(const double* __restrict__ Vt, const double* __restrict__ Ks
         if (lane < 4) sm.red[rw][cw * 32 + ni * 8 + 2 * lane + e] = v;
       }
     __syncthreads();
-    if (tid < TILE_ROWS)
-      ssqp[(size_t)split * chunk_cands + (size_t)t * TILE_ROWS + tid] =
-          sm.red[0][tid] + sm.red[1][tid];
+    if (tid < TILE_ROWS) {
+      const double tot = sm.red[0][tid] + sm.red[1][tid];
+      const int i = t * TILE_ROWS + tid;
+      if (fused) {   // one CTA saw every row block: finish mean / std / LogExp right here
+        if (i < fin.n_valid) finish_one(fin, i, true, tot);
+      } else {
+        ssqp[(size_t)split * chunk_cands + i] = tot;
+      }
+    }
     __syncthreads();
   }
 }
@@ -397,33 +443,13 @@ var_contract_kernel(const double* __restrict__ Vt, const double* __restrict__ Ks
 // ---------------------------------------------------------------------------------------
 // finish: gpr.py:1180-1195, 1207-1227 and LogExp.f acquisition_functions.py:1071-1074
 // ---------------------------------------------------------------------------------------
-__global__ void finish_kernel(const double* __restrict__ meanp, int JS,
-                              const double* __restrict__ ssqp, int row_splits, int chunk_cands,
-                              int n, double c, double y_mean, double y_std, double clip_hi,
-                              int want_acq, double two_zeta, double sigma_n2, double y_max,
-                              double* __restrict__ o_mean, double* __restrict__ o_std,
-                              double* __restrict__ o_acq) {
+__global__ void finish_kernel(FinishParams f, const double* __restrict__ ssqp, int row_splits) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double m_ = 0.0;
-  for (int s = 0; s < JS; s++) m_ += meanp[(size_t)s * chunk_cands + i];
-  double mean = m_ * y_std + y_mean;              // preprocessing.py:620
-  mean = fmin(mean, clip_hi);                     // gpr.py:1187-1195 (np.clip upper)
-  if (isnan(m_)) mean = m_;
-  if (o_mean) o_mean[i] = mean;
-  if (ssqp) {
-    double ssq = 0.0;
-    for (int s = 0; s < row_splits; s++) ssq += ssqp[(size_t)s * chunk_cands + i];
-    double var = c - ssq;                         // gpr.py:1207-1208
-    if (var < 0.0) var = 0.0;                     // :1214-1219
-    double std = sqrt(var) * y_std;               // :1220, preprocessing.py:630
-    if (o_std) o_std[i] = std;
-    if (want_acq && o_acq) {
-      double v = std * std - sigma_n2;            // std**2 - noise_level**2
-      v = v > 0.0 ? v : 0.0;                      // np.clip(., 0, None)
-      o_acq[i] = two_zeta * (mean - y_max) + log(sqrt(v));
-    }
-  }
+  if (i >= f.n_valid) return;
+  double ssq = 0.0;
+  if (ssqp)
+    for (int s = 0; s < row_splits; s++) ssq += ssqp[(size_t)s * f.chunk_cands + i];
+  finish_one(f, i, ssqp != nullptr, ssq);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -725,21 +751,31 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
       else
         launch_build_kind<false>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
     }
+    FinishParams fin;
+    fin.meanp = st->meanp.p;
+    fin.JS = JS;
+    fin.chunk_cands = chunk_cands;
+    fin.n_valid = n;
+    fin.c = st->c; fin.y_mean = st->y_mean; fin.y_std = st->y_std; fin.clip_hi = st->clip_hi;
+    fin.want_acq = want_acq ? 1 : 0;
+    fin.two_zeta = 2.0 * zeta; fin.sigma_n2 = sigma_n * sigma_n; fin.y_max = y_max;
+    fin.o_mean = d_mean ? d_mean + cand0 : nullptr;
+    fin.o_std = d_std ? d_std + cand0 : nullptr;
+    fin.o_acq = d_acq ? d_acq + cand0 : nullptr;
+    const bool fused = want_var && row_splits == 1;
     if (want_var) {
       TimedScope ts(st, s, T_CONTRACT);
       st->n_contract_launches += 1;
       dim3 grid(std::min(tiles, st->n_sm), row_splits);
       var_contract_kernel<<<grid, VC_THREADS, sizeof(VcSmem), s>>>(
-          st->Vt.p, st->Ks.p, tiles, st->N, st->nJ, st->nKT, row_splits, st->ssqp.p, chunk_cands);
+          st->Vt.p, st->Ks.p, tiles, st->N, st->nJ, st->nKT, row_splits, st->ssqp.p, chunk_cands,
+          fused ? 1 : 0, fin);
       GPRY_CUDA(cudaGetLastError());
     }
-    {
+    if (!fused) {
       TimedScope ts(st, s, T_FINISH);
-      finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(
-          st->meanp.p, JS, want_var ? st->ssqp.p : nullptr, row_splits, chunk_cands, n, st->c,
-          st->y_mean, st->y_std, st->clip_hi, want_acq ? 1 : 0, 2.0 * zeta, sigma_n * sigma_n,
-          y_max, d_mean ? d_mean + cand0 : nullptr,
-          d_std ? d_std + cand0 : nullptr, d_acq ? d_acq + cand0 : nullptr);
+      finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(fin, want_var ? st->ssqp.p : nullptr,
+                                                    row_splits);
       GPRY_CUDA(cudaGetLastError());
     }
   }
