@@ -223,10 +223,19 @@ def fit_state_for_bench(dev, N, d):
     return model
 
 
-def secondary_figures(dev, dev_t):
-    """BASELINE.json configs[3] and configs[4] on one GPU (device-event timed)."""
+def secondary_figures(dev, dev_t, world=1, dist=None):
+    """BASELINE.json configs[3] and configs[4]: every GPU works on its own share (restarts /
+    proposals split across ranks, no exchange); figures are whole-job (max time over ranks)."""
     import torch
     out = {}
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev_t)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # config D: LML + gradient, N_train = 4000, d = 20, 8 restarts' worth of theta per call
     N, d, B = 4000, 20, 8
@@ -240,9 +249,11 @@ def secondary_figures(dev, dev_t):
         t0 = time.perf_counter()
         lml, grad, info = dev.lml_batched("rbf", X, noise2, y_, thetas)
         dt = min(dt, time.perf_counter() - t0)
+    dt = max_over_ranks(dt)
     flop = N ** 3 + (3 * d + 4 + 2 * (d + 1)) * N ** 2 / 2
-    out["lml_grad"] = {"n_train": N, "dim": d, "batch": B, "evals_per_s": B / dt,
-                       "ms_per_eval": dt / B * 1e3, "tflops_algorithmic": flop * B / dt * 1e-12,
+    out["lml_grad"] = {"n_train": N, "dim": d, "restarts_per_gpu": B, "restarts_total": B * world,
+                       "evals_per_s": B * world / dt, "ms_per_eval_per_gpu": dt / B * 1e3,
+                       "tflops_algorithmic_per_gpu": flop * B / dt * 1e-12,
                        "all_pd": bool(np.all(info == 0))}
     # config E: mean-only proposals (surrogate MCMC), N_train = 2000, d = 16, 10^7 per step
     N, d, M = 2000, 16, 10_000_000
@@ -259,9 +270,9 @@ def secondary_figures(dev, dev_t):
         dev.predict(Xd, return_std=False, stream=s)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
-    out["mean_only"] = {"n_train": N, "dim": d, "proposals_per_step": M,
-                        "proposals_per_s": M / ms * 1e3, "ms_per_step": ms}
+    ms = max_over_ranks(e0.elapsed_time(e1) / 3)
+    out["mean_only"] = {"n_train": N, "dim": d, "proposals_per_step_per_gpu": M,
+                        "proposals_per_s": M * world / ms * 1e3, "ms_per_step": ms}
     return out
 
 
@@ -495,8 +506,8 @@ def run_ours(args):
     # ---- secondary figures of the same path (not the headline metric): LML+gradient
     # evaluations/s at config D and mean-only proposals/s at config E, this GPU only ----
     secondary = None
-    if rank == 0 and not args.no_secondary:
-        secondary = secondary_figures(dev, dev_t)
+    if not args.no_secondary:     # every rank runs them; rank 0 reports the whole-job figures
+        secondary = secondary_figures(dev, dev_t, world, dist if world > 1 else None)
 
     if rank == 0:
         line = {
@@ -521,10 +532,30 @@ def run_ours(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # Only the JSON line may reach stdout: libraries (NCCL prints its version banner there) are
+    # pointed at stderr for the duration of the run.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        import io
+        buf = io.StringIO()
+        real_stdout, sys.stdout = sys.stdout, buf
+        try:
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+        finally:
+            sys.stdout = real_stdout
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    out = buf.getvalue()
+    if out:
+        sys.stdout.write(out)
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":
