@@ -188,3 +188,33 @@ def test_lockstep_restart_driver_without_gpu():
     g.log_marginal_likelihood_batch = boom
     with pytest.raises(ValueError):
         g._lockstep_optimization(starts, box)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU arm) prints exactly one JSON line with the contract's
+    keys; it needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "1", "--cpu-chunk", "300",
+                          "--ntrain", "200", "--dim", "4"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "cpu_baseline", "e2e"):
+        assert key in d
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_build_entry_point():
+    """__graft_entry__.build() compiles the library (nvcc cross-compiles without a GPU)."""
+    import importlib
+    ge = importlib.import_module("__graft_entry__")
+    ge.build()
+    assert os.path.exists(os.path.join(ROOT, "gpry_b200", "libgpry_b200.so"))
