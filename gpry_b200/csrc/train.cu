@@ -29,6 +29,7 @@
 //                      dK/dtheta (N x N x (1+d)) is never materialised
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "state.cuh"
@@ -216,15 +217,10 @@ __device__ __forceinline__ void factor_inv_32(double* __restrict__ D, double* __
   for (int k = 0; k < SB; k++) Winv[k * SBLD + lane] = w[k];
 }
 
-__global__ void __launch_bounds__(256)
-potf2_inv_kernel(double* __restrict__ Aall, size_t sA, int ld, double* __restrict__ Wall, size_t sW,
-                 double* __restrict__ VTall, size_t sVT, int row_offset,
-                 int* __restrict__ info_all) {
-  double* A = Aall + blockIdx.x * sA;
-  double* W = Wall + blockIdx.x * sW;
-  double* VTd = VTall + blockIdx.x * sVT;
-  int* info = info_all + blockIdx.x;
-  extern __shared__ double sh[];
+__device__ __forceinline__ void potf2_inv_block(double* __restrict__ A, int ld,
+                                                double* __restrict__ W, double* __restrict__ VTd,
+                                                int row_offset, int* __restrict__ info,
+                                                double* __restrict__ sh) {
   double* Lb = sh;                       // 10 lower sub-blocks of the block / of L
   double* Wb = sh + 10 * SB_DOUBLES;     // 10 lower sub-blocks of the inverse
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -298,6 +294,17 @@ potf2_inv_kernel(double* __restrict__ Aall, size_t sA, int ld, double* __restric
   }
 }
 
+constexpr size_t POTF2_SMEM_DOUBLES = 20 * (size_t)SB_DOUBLES + 96;
+
+__global__ void __launch_bounds__(256)
+potf2_inv_kernel(double* __restrict__ Aall, size_t sA, int ld, double* __restrict__ Wall, size_t sW,
+                 double* __restrict__ VTall, size_t sVT, int row_offset,
+                 int* __restrict__ info_all) {
+  extern __shared__ double sh[];
+  potf2_inv_block(Aall + blockIdx.x * sA, ld, Wall + blockIdx.x * sW, VTall + blockIdx.x * sVT,
+                  row_offset, info_all + blockIdx.x, sh);
+}
+
 // ---------------------------------------------------------------------------------------
 // FP64 tensor-core GEMM, C (+)= alpha * A * B^T   (A: M x K, B: N x K, both k-contiguous),
 // batched over blockIdx.z, with up to two row segments that share the B operand.
@@ -323,6 +330,15 @@ struct GemmArgs {
   int n_tiles;          // 128-column tiles of C (rows of B)
   int K;                // multiple of 16
   int lower_only;       // only tiles with tile_row >= tile_col (segment 0)
+  // fused diagonal-block factorisation: the CTA that owns row tile 0 of segment 0 (the
+  // diagonal block of the panel update, dispatched first) goes on to factor and invert it
+  // while the other CTAs are still working on the rest of the panel
+  int fuse_potf2;
+  double* pW;           // [batch] 128 x 128 inverse blocks (stride sW)
+  double* pVT;          // [batch] diagonal block of V^T (stride sVT, leading dimension ldc of seg 0)
+  size_t sW, sVT;
+  int row_offset;
+  int* info;
 };
 
 struct GemmSmem {
@@ -429,18 +445,26 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
       }
       *cp = v;
     }
+  if (g.fuse_potf2 && si == 0 && mt == 0) {
+    __threadfence_block();
+    __syncthreads();                     // the whole updated block is in global memory
+    potf2_inv_block(Cg, ldc, g.pW + bz * g.sW, g.pVT + bz * g.sVT, g.row_offset, g.info + bz,
+                    reinterpret_cast<double*>(smem_raw));
+  }
 }
 
 static void launch_gemm(const GemmArgs& g, int batch, cudaStream_t s) {
   const int mt = g.seg[0].m_tiles + g.seg[1].m_tiles;
   if (mt <= 0 || g.n_tiles <= 0 || g.K <= 0 || batch <= 0) return;
   dim3 grid(batch, mt, g.n_tiles);
-  gemm_nt_kernel<<<grid, G_THREADS, sizeof(GemmSmem), s>>>(g);
+  const size_t smem = g.fuse_potf2 ? std::max(sizeof(GemmSmem), POTF2_SMEM_DOUBLES * 8)
+                                   : sizeof(GemmSmem);
+  gemm_nt_kernel<<<grid, G_THREADS, smem, s>>>(g);
   GPRY_CUDA(cudaGetLastError());
 }
 static void gemm_prepare() {
   GPRY_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(GemmSmem)));
+                                 (int)std::max(sizeof(GemmSmem), POTF2_SMEM_DOUBLES * 8)));
 }
 
 void gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N,
@@ -780,7 +804,7 @@ static void factorize_batch(gpry_state* st, TrainBuffers& b, int kind, const dou
     default: launch_kmat<GPRY_KERNEL_MATERN25>(b, nth, s);
   }
   gemm_prepare();
-  const size_t potf2_smem = (20 * (size_t)SB_DOUBLES + 96) * 8;
+  const size_t potf2_smem = POTF2_SMEM_DOUBLES * 8;
   GPRY_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)potf2_smem));
   const size_t sWinv = (size_t)nb * NB * NB, sTT = (size_t)Np * NB;
@@ -788,19 +812,24 @@ static void factorize_batch(gpry_state* st, TrainBuffers& b, int kind, const dou
     const size_t jB = (size_t)j * NB;
     if (j > 0) {
       // (1) block column j of A minus the contribution of the finished columns, and the
-      //     V^T row-sweep product, sharing the B operand L[j, :j]
+      //     V^T row-sweep product, sharing the B operand L[j, :j];  (2) the CTA of the diagonal
+      //     tile then factors and inverts it (potf2_inv_block) inside the same launch
       GemmArgs g{};
       g.seg[0] = GemmSeg{b.K + jB * Np, b.K + jB * Np + jB, Np, Np, nb - j, -1.0, 1, 0, NN, NN};
       g.seg[1] = GemmSeg{b.VT, b.TT, Np, NB, j, 1.0, 0, 1, NN, sTT};
       g.B = b.K + jB * Np; g.ldb = Np; g.sB = NN;
       g.n_tiles = 1; g.K = (int)jB; g.lower_only = 0;
+      g.fuse_potf2 = 1;
+      g.pW = b.Winv + jB * NB; g.sW = sWinv;
+      g.pVT = b.VT + jB * (Np + 1); g.sVT = NN;
+      g.row_offset = (int)jB; g.info = b.info;
       launch_gemm(g, nth, s);
+    } else {
+      // (2) first diagonal block: nothing to subtract
+      potf2_inv_kernel<<<nth, 256, potf2_smem, s>>>(b.K, NN, Np, b.Winv, sWinv, b.VT, NN, 0,
+                                                    b.info);
+      GPRY_CUDA(cudaGetLastError());
     }
-    // (2) diagonal block
-    potf2_inv_kernel<<<nth, 256, potf2_smem, s>>>(b.K + jB * (Np + 1), NN, Np,
-                                                  b.Winv + jB * NB, sWinv,
-                                                  b.VT + jB * (Np + 1), NN, (int)jB, b.info);
-    GPRY_CUDA(cudaGetLastError());
     // (3) panel solve and the new block column of V^T, sharing the B operand W_jj
     if (nb - j - 1 > 0 || j > 0) {
       GemmArgs g{};
