@@ -204,7 +204,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
-def fit_state_for_bench(dev, N, d):
+def fit_state_for_bench(dev, N, d, kind="rbf"):
     """Training state for the synthetic problem: Normalize_bounds / Normalize_y scalars on the
     host (O(N)), kernel matrix + Cholesky + L^-1 + alpha on the GPU (gpry_factorize)."""
     X, y, theta, bounds = synthetic_problem(N, d)
@@ -213,10 +213,10 @@ def fit_state_for_bench(dev, N, d):
     X_ = (X - bounds[:, 0]) / (bounds[:, 1] - bounds[:, 0])
     y_ = (y - y_mean) / y_std
     noise2 = np.full(N, (noise_level / y_std) ** 2)
-    L, V, alpha_, _, info = dev.factorize("rbf", X_, noise2, y_, theta, want_L=False)
+    L, V, alpha_, _, info = dev.factorize(kind, X_, noise2, y_, theta, want_L=False)
     assert info == 0, "synthetic kernel matrix not positive definite"
     clip_hi = 1.1 * y.max() - 0.1 * y.min()
-    model = dict(kind="rbf", X_=X_, alpha_=alpha_, V=V, c=float(np.exp(theta[0])),
+    model = dict(kind=kind, X_=X_, alpha_=alpha_, V=V, c=float(np.exp(theta[0])),
                  ell=np.exp(theta[1:]), x_min=bounds[:, 0], x_width=bounds[:, 1] - bounds[:, 0],
                  y_mean=y_mean, y_std=y_std, clip_hi=clip_hi, y_max=float(y.max()),
                  noise_level=noise_level, zeta=float(d) ** -0.85)
@@ -271,6 +271,25 @@ def secondary_figures(dev, dev_t, world=1, dist=None):
     e1.record()
     torch.cuda.synchronize()
     ms = max_over_ranks(e0.elapsed_time(e1) / 3)
+    del Xd
+    # config B (and its Matern-5/2 repeat): N_train = 1000, d = 8, 10^6 candidates, mean+std+acq
+    for kind in ("rbf", "matern25"):
+        Nb, db, Mb = 1000, 8, 1_000_000
+        mb = fit_state_for_bench(dev, Nb, db, kind)
+        dev.upload(mb["kind"], mb["X_"], mb["alpha_"], mb["V"], mb["c"], mb["ell"], mb["x_min"],
+                   mb["x_width"], mb["y_mean"], mb["y_std"], mb["clip_hi"])
+        Xb = torch.rand((Mb, db), dtype=torch.float64, device=dev_t)
+        dev.predict_logexp(Xb, mb["zeta"], mb["noise_level"], mb["y_max"], stream=s)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            dev.predict_logexp(Xb, mb["zeta"], mb["noise_level"], mb["y_max"], stream=s)
+        e1.record()
+        torch.cuda.synchronize()
+        msb = max_over_ranks(e0.elapsed_time(e1) / 3)
+        out["config_b_" + kind] = {"n_train": Nb, "dim": db, "candidates_per_gpu": Mb,
+                                   "candidates_per_s": Mb * world / msb * 1e3, "ms_per_step": msb}
+        del Xb
     out["mean_only"] = {"n_train": N, "dim": d, "proposals_per_step_per_gpu": M,
                         "proposals_per_s": M * world / ms * 1e3, "ms_per_step": ms}
     return out

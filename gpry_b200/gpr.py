@@ -657,8 +657,8 @@ class GaussianProcessRegressor:
                 return_std_grad=False, validate=True, ignore_trust_region=False):
         """gpr.py:1022-1273."""
         self.n_eval += len(X)
-        if return_cov:
-            raise NotImplementedError("return_cov is not part of the B200 path")
+        # NB: ``return_cov`` is accepted and ignored, exactly as in the reference (its body
+        # never reads the argument, gpr.py:1022-1273)
         if return_std_grad and not (return_std and return_mean_grad):
             raise ValueError("Not returning std_gradient without returning the std and the "
                              "mean grad.")

@@ -53,7 +53,7 @@ def make_reference_gpr(gpry, kind, X, y, theta, bounds, noise_level=1e-2, normal
 
 
 def case(gpry, name, kind, N, d, M, seed, ell, c=1.0, bounds=None, normalize=True,
-         with_lml=True, pool=None, noise_level=1e-2, store_train=True):
+         with_lml=True, pool=None, noise_level=1e-2, store_train=True, clip_factor=1.1):
     rng = np.random.default_rng(seed)
     if bounds is None:
         bounds = np.array([[0.0, 1.0]] * d)
@@ -63,7 +63,8 @@ def case(gpry, name, kind, N, d, M, seed, ell, c=1.0, bounds=None, normalize=Tru
     y = target(U)
     Xc = lo + rng.uniform(size=(M, d)) * (hi - lo)
     theta = np.log(np.concatenate([[c], np.full(d, ell) * (1 + 0.1 * np.arange(d) / d)]))
-    gpr = make_reference_gpr(gpry, kind, X, y, theta, bounds, noise_level, normalize)
+    gpr = make_reference_gpr(gpry, kind, X, y, theta, bounds, noise_level, normalize,
+                             clip_factor=clip_factor)
     mean, std = gpr.predict(Xc, return_std=True, validate=False)
     std_only = gpr.predict_std(Xc, validate=False)
     mean_only = gpr.predict(Xc, validate=False)
@@ -76,7 +77,8 @@ def case(gpry, name, kind, N, d, M, seed, ell, c=1.0, bounds=None, normalize=Tru
                                  return_std_grad=True, validate=False)
     out = dict(
         kind=kind, N=N, d=d, M=M, seed=seed, theta=theta, bounds=bounds,
-        noise_level=noise_level, normalize=normalize, zeta=zeta,
+        noise_level=noise_level, normalize=normalize, zeta=zeta, clip_factor=clip_factor,
+        n_clipped=int(np.sum(mean >= clip_factor * max(y) - (clip_factor - 1) * min(y))),
         Xc=Xc, mean=mean, std=std, std_only=std_only, mean_only=mean_only,
         acq_f=acq_f, acq_call=acq_call, grad_mean=gm, grad_std=gs,
         y_mean=getattr(gpr.preprocessing_y, "mean_", 0.0),
@@ -228,6 +230,9 @@ def main():
     case(gpry, "rbf_d3_n100_raw", "rbf", 100, 3, 128, 16, 0.4, normalize=False)
     case(gpry, "rbf_d8_n1000", "rbf", 1000, 8, 512, 1234, 0.5, with_lml=False,
          store_train=False)
+    # upper clipping of the mean active (clip_factor = 1: nothing may exceed max(y_train))
+    case(gpry, "rbf_d4_n150_clip1", "rbf", 150, 4, 2048, 18, 0.35, with_lml=False,
+         clip_factor=1.0)
     nonpd_case(gpry)
     fit_case(gpry)
     loop_case(gpry)

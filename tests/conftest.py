@@ -32,6 +32,7 @@ def load_golden(name):
     g["normalize"] = bool(g["normalize"])
     g["noise_level"] = float(g["noise_level"])
     g["zeta"] = float(g["zeta"])
+    g["clip_factor"] = float(g["clip_factor"]) if "clip_factor" in g else 1.1
     if "X_train" not in g:  # regenerate from the seed exactly as oracle/gen_golden.py does
         rng = np.random.default_rng(g["seed"])
         lo, hi = g["bounds"][:, 0], g["bounds"][:, 1]
@@ -51,7 +52,8 @@ def oracle_state(g):
     from oracle import gp_oracle as orc
     return orc.GPState(g["kind"], g["theta"], g["X_train"], g["y_train"],
                        bounds=g["bounds"] if g["normalize"] else None,
-                       normalize_y=g["normalize"], noise_level=g["noise_level"])
+                       normalize_y=g["normalize"], noise_level=g["noise_level"],
+                       clip_factor=g["clip_factor"])
 
 
 def scaled_err(a, b, scale):

@@ -24,6 +24,7 @@ def make_gpr(g, **kw):
     norm = g["normalize"]
     gpr = GaussianProcessRegressor(
         kernel=kernel, bounds=g["bounds"], noise_level=g["noise_level"],
+        clip_factor=g["clip_factor"],
         preprocessing_X=Normalize_bounds(g["bounds"]) if norm else None,
         preprocessing_y=Normalize_y() if norm else None, account_for_inf=None, verbose=0, **kw)
     gpr.kernel_ = deepcopy(gpr.kernel)
