@@ -7,6 +7,7 @@ This is the thin layer between the reference-shaped Python classes (``gpry_b200.
 device pointers are handed over, nothing is copied).
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -27,14 +28,16 @@ def _stream_ptr(stream):
 
 
 _workspaces = {}
+_workspaces_lock = threading.Lock()
 
 
 def workspace(device=0):
     """Process-wide DeviceGP whose big training-side buffers are shared by every regressor
     instance of this process (factorizations, LML, stand-alone kernel evaluations)."""
-    if device not in _workspaces:
-        _workspaces[device] = DeviceGP(device)
-    return _workspaces[device]
+    with _workspaces_lock:
+        if device not in _workspaces:
+            _workspaces[device] = DeviceGP(device)
+        return _workspaces[device]
 
 
 class DeviceGP:

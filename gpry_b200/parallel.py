@@ -142,10 +142,6 @@ def max_scalar(x):
     return float(t.item())
 
 
-def any_true(flag):
-    return max_scalar(1.0 if flag else 0.0) > 0.0
-
-
 def allgather_survivors(acq, idx, mean, std, X):
     """All-gather of the per-rank survivor records (acq, idx, mean, std, X[K', d]) so that every
     rank holds the union (replaces gp_acquisition.py:1148-1171 + bcast :1190).  Ragged counts
