@@ -716,12 +716,154 @@ static int choose_jsplit(const gpry_state* st, int tiles) {
   return JS;
 }
 
+// ---------------------------------------------------------------------------------------
+// Latency path for a handful of candidates (M <= SMALL_M_MAX: single-point calls of samplers and
+// optimisers, predict_std on a few pool rows): no 128-wide tiles, V is streamed once.
+//   small_kstar   ks[m][j] = k(x_m, X_j)                      (thread per training point)
+//   small_vk      u[m][j]  = sum_k V[j][k] ks[m][k]           (warp per row of V, M accumulators)
+//   small_finish  mean_m = sum_j ks[m][j] alpha_j, ssq_m = sum_j u[m][j]^2, then finish_one
+// ---------------------------------------------------------------------------------------
+constexpr int SMALL_M = 8;        // candidates per pass over V
+constexpr int SMALL_M_MAX = 64;   // largest batch served by this path
+
+template <int KIND>
+__global__ void small_kstar_kernel(const double* __restrict__ X, int M, int d,
+                                   const double* __restrict__ T, int N, int Np, int DP,
+                                   const double* __restrict__ prm, double c,
+                                   double* __restrict__ ks) {
+  __shared__ double us[SMALL_M * MAX_DIM];
+  for (int e = threadIdx.x; e < M * DP; e += blockDim.x) {
+    int m = e / DP, k = e % DP;
+    double v = 0.0;
+    if (k < d) {
+      double x = X[(size_t)m * d + k];
+      v = ((x - prm[k]) / prm[MAX_DIM + k]) / prm[2 * MAX_DIM + k];
+    }
+    us[m * MAX_DIM + k] = v;
+  }
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Np) return;
+  for (int m = 0; m < M; m++) {
+    double v = 0.0;
+    if (j < N) {
+      double r2 = 0.0;
+      for (int k = 0; k < DP; k++) {
+        double df = us[m * MAX_DIM + k] - T[(size_t)j * DP + k];
+        r2 = fma(df, df, r2);
+      }
+      v = kernel_value<KIND>(r2, c);
+    }
+    ks[(size_t)m * Np + j] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+small_vk_kernel(const double* __restrict__ V, int Np, int N, const double* __restrict__ ks, int M,
+                double* __restrict__ u) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (j >= Np) return;
+  double acc[SMALL_M];
+#pragma unroll
+  for (int m = 0; m < SMALL_M; m++) acc[m] = 0.0;
+  if (j < N) {
+    for (int k = lane; k <= j; k += 32) {
+      const double v = V[(size_t)j * Np + k];
+#pragma unroll
+      for (int m = 0; m < SMALL_M; m++)
+        if (m < M) acc[m] = fma(v, ks[(size_t)m * Np + k], acc[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < SMALL_M; m++) {
+    double v = acc[m];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && m < M) u[(size_t)m * Np + j] = v;
+  }
+}
+
+// one block per candidate
+__global__ void __launch_bounds__(256)
+small_finish_kernel(const double* __restrict__ ks, const double* __restrict__ u,
+                    const double* __restrict__ alpha, int N, int Np, int have_var,
+                    FinishParams f, double* __restrict__ meanp_out) {
+  __shared__ double r0[256], r1[256];
+  const int m = blockIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int j = threadIdx.x; j < N; j += 256) {
+    a = fma(ks[(size_t)m * Np + j], alpha[j], a);
+    if (have_var) {
+      double uu = u[(size_t)m * Np + j];
+      b = fma(uu, uu, b);
+    }
+  }
+  r0[threadIdx.x] = a;
+  r1[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      r0[threadIdx.x] += r0[threadIdx.x + o];
+      r1[threadIdx.x] += r1[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    meanp_out[m] = r0[0];          // f.meanp points here with JS = 1
+    finish_one(f, m, have_var != 0, r1[0]);
+  }
+}
+
+static void predict_small(gpry_state* st, const double* dX, int M, bool want_var, bool want_acq,
+                          double zeta, double sigma_n, double y_max, double* d_mean,
+                          double* d_std, double* d_acq, cudaStream_t s) {
+  const int N = st->N, Np = st->Npad, DP = st->DP, d = st->d;
+  st->pc_U.reserve((size_t)(2 * SMALL_M) * Np + SMALL_M);
+  double* ks = st->pc_U.p;
+  double* u = ks + (size_t)SMALL_M * Np;
+  double* mp = u + (size_t)SMALL_M * Np;
+  TimedScope ts(st, s, T_BUILD, 3);
+  const int nblk = (Np + 127) / 128;
+  switch (st->kind) {
+    case GPRY_KERNEL_RBF:
+      small_kstar_kernel<GPRY_KERNEL_RBF><<<nblk, 128, 0, s>>>(dX, M, d, st->T.p, N, Np, DP,
+                                                              st->prm_dev.p, st->c, ks);
+      break;
+    case GPRY_KERNEL_MATERN15:
+      small_kstar_kernel<GPRY_KERNEL_MATERN15><<<nblk, 128, 0, s>>>(dX, M, d, st->T.p, N, Np, DP,
+                                                                   st->prm_dev.p, st->c, ks);
+      break;
+    default:
+      small_kstar_kernel<GPRY_KERNEL_MATERN25><<<nblk, 128, 0, s>>>(dX, M, d, st->T.p, N, Np, DP,
+                                                                   st->prm_dev.p, st->c, ks);
+  }
+  GPRY_CUDA(cudaGetLastError());
+  if (want_var) {
+    small_vk_kernel<<<(Np * 32 + 255) / 256, 256, 0, s>>>(st->Vrm.p, Np, N, ks, M, u);
+    GPRY_CUDA(cudaGetLastError());
+  }
+  FinishParams fin;
+  fin.meanp = mp; fin.JS = 1; fin.chunk_cands = SMALL_M; fin.n_valid = M;
+  fin.c = st->c; fin.y_mean = st->y_mean; fin.y_std = st->y_std; fin.clip_hi = st->clip_hi;
+  fin.want_acq = want_acq ? 1 : 0;
+  fin.two_zeta = 2.0 * zeta; fin.sigma_n2 = sigma_n * sigma_n; fin.y_max = y_max;
+  fin.o_mean = d_mean; fin.o_std = d_std; fin.o_acq = d_acq;
+  small_finish_kernel<<<M, 256, 0, s>>>(ks, u, st->alpha.p, N, Np, want_var ? 1 : 0, fin, mp);
+  GPRY_CUDA(cudaGetLastError());
+}
+
 void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mean, bool want_var,
                       bool want_acq, double zeta, double sigma_n, double y_max, double* d_mean,
                       double* d_std, double* d_acq, cudaStream_t s) {
   if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
   if (M <= 0) return;
   GPRY_CUDA(cudaSetDevice(st->device));
+  if (M <= SMALL_M_MAX) {   // latency path, SMALL_M candidates per pass over V
+    for (int m0 = 0; m0 < (int)M; m0 += SMALL_M)
+      predict_small(st, dX + (size_t)m0 * st->d, std::min(SMALL_M, (int)M - m0), want_var, want_acq,
+                    zeta, sigma_n, y_max, d_mean ? d_mean + m0 : nullptr,
+                    d_std ? d_std + m0 : nullptr, d_acq ? d_acq + m0 : nullptr, s);
+    return;
+  }
   const int64_t total_tiles = (M + TILE_ROWS - 1) / TILE_ROWS;
   // chunking: at most 2 waves of tiles per chunk (bounds the K* scratch: 2 MB/tile at N=2048)
   const int max_chunk_tiles = 2 * st->n_sm;

@@ -122,6 +122,28 @@ def test_small_and_ragged(dev):
     assert len(a) == 5 and sorted(idx.tolist()) == [0, 1, 2, 3, 4]
 
 
+@pytest.mark.parametrize("kind", ["rbf", "matern15", "matern25"])
+def test_latency_path_small_batches(dev, kind):
+    """M <= 64 takes the GEMV-style latency path; it must agree with the oracle and (to
+    round-off) with the tiled path used for larger batches."""
+    X, y, theta, bounds = orc.synthetic_problem(900, 7)
+    st = orc.GPState(kind, theta, X, y, bounds=bounds)
+    upload_from_oracle(dev, st)
+    Xc = np.random.default_rng(5).uniform(size=(100, 7))
+    mo, so, ao = orc.predict_logexp(st, Xc, zeta=0.3)
+    mb, sb, ab = dev.predict_logexp(Xc, 0.3, st.noise_level, st.y_max)      # tiled path
+    for M in (1, 2, 3, 7, 8, 9, 17, 40, 64):
+        m, s_, a = dev.predict_logexp(Xc[:M], 0.3, st.noise_level, st.y_max)
+        assert scaled_err(m, mo[:M], st.y_std) < TOL
+        assert scaled_err(s_ ** 2, so[:M] ** 2, st.y_std ** 2) < TOL
+        assert scaled_err(m, mb[:M], st.y_std) < 1e-12
+        assert scaled_err(s_ ** 2, sb[:M] ** 2, st.y_std ** 2) < 1e-12
+        m1, none = dev.predict(Xc[:M])
+        assert none is None and np.array_equal(m1, m)
+        _, s2 = dev.predict(Xc[:M], return_mean=False, return_std=True)
+        assert np.array_equal(s2, s_)
+
+
 def test_device_pointers(dev):
     import torch
     X, y, theta, bounds = orc.synthetic_problem(400, 6)
