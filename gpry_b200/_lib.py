@@ -35,6 +35,7 @@ SIGNATURES = {
     "gpry_state_adopt_factorization": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_double,
                                                  C.c_double, C.c_double]),
+    "gpry_set_trust_region": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double]),
     "gpry_state_info": (C.c_int, [C.c_void_p, _c_int_p, _c_int_p, _c_int_p]),
     "gpry_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_void_p]),

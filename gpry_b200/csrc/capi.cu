@@ -171,7 +171,7 @@ int gpry_state_destroy(gpry_state* st) {
     st->Vt.release(); st->Ks.release(); st->meanp.release(); st->ssqp.release();
     st->Xdev.release(); st->o_mean.release(); st->o_std.release(); st->o_acq.release();
     for (int b = 0; b < 2; b++) { st->tk_keys[b].release(); st->tk_idx[b].release(); }
-    st->tmp.release(); st->small.release(); st->Vrm.release();
+    st->tmp.release(); st->small.release(); st->Vrm.release(); st->trust.release();
     st->pc_U.release(); st->pc_Ks.release(); st->pc_UT.release(); st->pc_G.release();
     st->f_K.release(); st->f_VT.release(); st->f_W.release(); st->f_TT.release();
     st->f_Winv.release(); st->f_misc.release(); st->f_prob.release();
@@ -208,6 +208,28 @@ int gpry_state_adopt_factorization(gpry_state* st, double c, const double* ell,
   });
 }
 
+int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const double* upper,
+                          double value) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    if (!lower || !upper) {
+      st->trust_on = false;
+      return;
+    }
+    GPRY_CHECK_ARG(d >= 1 && d <= MAX_DIM, "bad dimensionality");
+    GPRY_CUDA(cudaSetDevice(st->device));
+    std::vector<double> h(2 * MAX_DIM, 0.0);
+    for (int k = 0; k < d; k++) {
+      h[k] = lower[k];
+      h[MAX_DIM + k] = upper[k];
+    }
+    st->trust.reserve(2 * MAX_DIM);
+    GPRY_CUDA(cudaMemcpy(st->trust.p, h.data(), 2 * MAX_DIM * 8, cudaMemcpyHostToDevice));
+    st->trust_value = value;
+    st->trust_on = true;
+  });
+}
+
 int gpry_state_info(const gpry_state* st, int* N, int* d, int* kind) {
   if (!st || !st->loaded) {
     set_last_error("no model uploaded into this state");
@@ -222,7 +244,7 @@ int gpry_state_info(const gpry_state* st, int* N, int* d, int* kind) {
 static void predict_common(gpry_state* st, const double* X, int64_t M, bool want_mean,
                            bool want_std, bool want_acq, double zeta, double sigma_n, double y_max,
                            int where, double* out_mean, double* out_std, double* out_acq,
-                           cudaStream_t s) {
+                           cudaStream_t s, bool trust = false) {
   GPRY_CHECK_ARG(st != nullptr, "state is NULL");
   if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
   GPRY_CHECK_ARG(M >= 0, "M < 0");
@@ -244,6 +266,7 @@ static void predict_common(gpry_state* st, const double* X, int64_t M, bool want
   const double* dX = nullptr;
   run_pipeline_blocks(st, X, M, x_dev, need_var, da != nullptr, zeta, sigma_n, y_max, dm, ds, da,
                       &dX, s);
+  if (trust) apply_trust_region(st, dX, M, dm, s);
   if (!o_dev) {
     TimedScope ts(st, s, T_D2H, 0);
     if (dm) GPRY_CUDA(cudaMemcpyAsync(out_mean, dm, M * 8, cudaMemcpyDeviceToHost, s));
@@ -258,7 +281,7 @@ int gpry_predict(gpry_state* st, const double* X, int64_t M, int what, int where
                  double* out_mean, double* out_std, void* stream) {
   return guarded([&] {
     predict_common(st, X, M, what & GPRY_WANT_MEAN, what & GPRY_WANT_STD, false, 0, 0, 0, where,
-                   out_mean, out_std, nullptr, (cudaStream_t)stream);
+                   out_mean, out_std, nullptr, (cudaStream_t)stream, true);
   });
 }
 

@@ -851,6 +851,29 @@ static void predict_small(gpry_state* st, const double* dX, int M, bool want_var
   GPRY_CUDA(cudaGetLastError());
 }
 
+// mean[i] = value for candidates outside [lo, hi] (tools.py:263-287 is_in_bounds, gpr.py:1201)
+__global__ void trust_mask_kernel(const double* __restrict__ X, int64_t M, int d,
+                                  const double* __restrict__ lohi, double value,
+                                  double* __restrict__ mean) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  bool inside = true;
+  for (int k = 0; k < d; k++) {
+    double x = X[i * d + k];
+    inside = inside && (x >= lohi[k]) && (x <= lohi[MAX_DIM + k]);
+  }
+  if (!inside) mean[i] = value;
+}
+
+void apply_trust_region(gpry_state* st, const double* dX, int64_t M, double* d_mean,
+                        cudaStream_t s) {
+  if (!st->trust_on || !d_mean || M <= 0) return;
+  TimedScope ts(st, s, T_FINISH);
+  trust_mask_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(dX, M, st->d, st->trust.p,
+                                                               st->trust_value, d_mean);
+  GPRY_CUDA(cudaGetLastError());
+}
+
 void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mean, bool want_var,
                       bool want_acq, double zeta, double sigma_n, double y_max, double* d_mean,
                       double* d_std, double* d_acq, cudaStream_t s) {

@@ -69,6 +69,10 @@ struct gpry_state {
   int nJ = 0;     // row blocks of V (Npad / 128)
   int nKT = 0;    // k-tiles per candidate tile (Npad / 16)
   double c = 1.0, y_mean = 0.0, y_std = 1.0, clip_hi = 0.0;
+  // optional trust region applied to the mean on the device (gpr.py:1104-1109, 1200-1201)
+  bool trust_on = false;
+  double trust_value = 0.0;
+  gpry::DevBuf<double> trust;            // [2][MAX_DIM] lower, upper (un-transformed)
   gpry::XformParams prm;                 // valid when d <= MAX_DIM_REG
   gpry::DevBuf<double> prm_dev;          // [3][MAX_DIM] x_min, x_width, ell (generic-d path)
   gpry::DevBuf<double> T;                // [Npad][DP]  X_train_ / ell   (zero padded)
@@ -126,6 +130,8 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
                       bool want_var, bool want_acq, double zeta, double sigma_n, double y_max,
                       double* d_mean, double* d_std, double* d_acq, cudaStream_t s);
 void mean_grad_device(gpry_state* st, const double* x_host, double* out_host);
+void apply_trust_region(gpry_state* st, const double* dX, int64_t M, double* d_mean,
+                        cudaStream_t s);
 void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                   const double* alpha_, const double* V_host, const double* V_dev_rowmajor,
                   const double* VT_dev_rowmajor, int ldV, const double* alpha_dev, double c,

@@ -94,6 +94,16 @@ class DeviceGP:
             float(y_std), float(clip_hi)))
         self.N, self.d, self.kind = self._f_N, d, self._f_kind
 
+    def set_trust_region(self, bounds=None, value=-np.inf):
+        """Device-side trust region for ``predict``'s mean: (d, 2) bounds or None to clear."""
+        if bounds is None:
+            check(self._lib.gpry_set_trust_region(self._h, 0, None, None, 0.0))
+            return
+        b = as_f64(bounds)
+        lo, hi = np.ascontiguousarray(b[:, 0]), np.ascontiguousarray(b[:, 1])
+        check(self._lib.gpry_set_trust_region(self._h, b.shape[0], ptr(lo), ptr(hi),
+                                              float(value)))
+
     # ------------------------------------------------------------------ candidate side
     def _prep_X(self, X):
         if self.kind is None:

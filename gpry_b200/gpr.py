@@ -666,8 +666,11 @@ class GaussianProcessRegressor:
             raise ValueError("Mean grad and std grad not implemented for n_samples > 1")
         X = self._as_2d(X, validate)
         impose_trust_region = self.trust_bounds is not None and not ignore_trust_region
+        # without a classifier the trust-region mask is applied on the device (no O(M d) host
+        # pass over large pools); with one, rows are re-packed on the host anyway
+        trust_on_device = impose_trust_region and self.infinities_classifier is None
         i_outside_trust = None
-        if impose_trust_region:
+        if impose_trust_region and not trust_on_device:
             i_outside_trust = np.logical_not(is_in_bounds(X, self.trust_bounds))
         finite = None
         if self.infinities_classifier is not None:   # gpr.py:1136-1174
@@ -694,11 +697,13 @@ class GaussianProcessRegressor:
             grad_mean_full[~finite] = self.inf_value
             X = X[finite]
         dev = self._device_state()
+        dev.set_trust_region(self.trust_bounds if trust_on_device else None,
+                             self.minus_inf_value)
         y_mean, y_std = dev.predict(X, return_mean=True, return_std=return_std)
         if finite is not None:
             y_mean_full[finite] = y_mean
             y_mean = y_mean_full
-        if impose_trust_region:
+        if impose_trust_region and not trust_on_device:
             y_mean[i_outside_trust] = self.minus_inf_value
         if return_std:
             if finite is not None:

@@ -101,6 +101,13 @@ int gpry_state_adopt_factorization(gpry_state* st, double c, const double* ell,
                                    const double* x_min, const double* x_width,
                                    double y_mean, double y_std, double clip_hi);
 
+/* Trust region applied ON THE DEVICE to the mean returned by gpry_predict (not to the std, not
+ * to the acquisition entry points): candidates outside [lower, upper] (un-transformed, d
+ * entries each, host pointers) get mean = value (gpr.py:1104-1109, 1200-1201 with
+ * tools.py:263-287).  lower = upper = NULL switches it off.  Stays set across uploads. */
+int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const double* upper,
+                          double value);
+
 /* Query what is loaded: N, d, kind (any may be NULL). Returns GPRY_ERR_STATE if empty. */
 int gpry_state_info(const gpry_state* st, int* N, int* d, int* kind);
 

@@ -334,3 +334,47 @@ def test_classifier_and_trust_region_masks():
     all_inf = np.tile(g["bounds"][:, 1], (3, 1))        # x_0 = 1 > 0.9 for every row
     m3, s3 = gpr.predict(all_inf, return_std=True)
     assert np.all(m3 == -1e300) and np.all(s3 == 0)
+
+
+def test_trust_region_mask_on_device():
+    """Without a classifier the trust-region mask (gpr.py:1104-1109, 1200-1201; inclusive bounds
+    as tools.py:287) is applied by the library: same rows, same values as the host mask, std
+    untouched, ignore_trust_region / predict_std / the acquisition calls unaffected."""
+    from gpry_b200.gpr import GaussianProcessRegressor
+    from gpry_b200.preprocessing import Normalize_bounds, Normalize_y
+    g = load_golden("rbf_d8_n300")
+    plain = make_gpr(g)
+    gpr = GaussianProcessRegressor(
+        kernel="RBF", bounds=g["bounds"], noise_level=g["noise_level"],
+        preprocessing_X=Normalize_bounds(g["bounds"]), preprocessing_y=Normalize_y(),
+        account_for_inf=None, verbose=0, trust_region_factor=0.5)
+    gpr.kernel_ = deepcopy(gpr.kernel)
+    gpr.kernel_.theta = g["theta"]
+    gpr.append_to_data(g["X_train"], g["y_train"], fit_gpr=False)
+    tb = gpr.trust_bounds
+    assert tb is not None
+    rng = np.random.default_rng(5)
+    lo, hi = g["bounds"][:, 0], g["bounds"][:, 1]
+    Xc = lo + (hi - lo) * rng.random((20000, g["d"]))
+    Xc[0] = tb[:, 0]                        # exactly on the lower corner: inside
+    Xc[1] = tb[:, 1]                        # exactly on the upper corner: inside
+    Xc[2] = tb[:, 1]
+    Xc[2, 3] = np.nextafter(tb[3, 1], np.inf)   # one ulp outside in one coordinate
+    out = ~np.all((Xc >= tb[:, 0]) & (Xc <= tb[:, 1]), axis=1)
+    assert out.any() and (~out).any() and not out[0] and not out[1] and out[2]
+    ref_m, ref_s = plain.predict(Xc, return_std=True)
+    m, s = gpr.predict(Xc, return_std=True)
+    assert np.all(m[out] == -np.inf) and np.array_equal(m[~out], ref_m[~out])
+    assert np.array_equal(s, ref_s)
+    assert np.array_equal(gpr.predict(Xc, ignore_trust_region=True), ref_m)
+    assert np.array_equal(gpr.predict_std(Xc), ref_s)
+    gpr.minus_inf_value = -1e300
+    assert np.all(gpr.predict(Xc)[out] == -1e300)
+    for Msmall in (1, 5, 64):               # latency path
+        mm = gpr.predict(Xc[:Msmall])
+        assert np.array_equal(mm[~out[:Msmall]], plain.predict(Xc[:Msmall])[~out[:Msmall]])
+        assert np.all(mm[out[:Msmall]] == -1e300)
+    zeta, sn = 1.3, gpr.noise_level
+    a0 = plain.predict_logexp(Xc, zeta, sn)[2]
+    a1 = gpr.predict_logexp(Xc, zeta, sn)[2]
+    assert np.array_equal(a0, a1)
