@@ -272,6 +272,25 @@ def secondary_figures(dev, dev_t, world=1, dist=None):
     torch.cuda.synchronize()
     ms = max_over_ranks(e0.elapsed_time(e1) / 3)
     del Xd
+    # same model: batched gradients for the acquisition optimiser's restarts (host in / out,
+    # as the lock-step L-BFGS-B drivers call it) and the one-point latency path
+    Xg = np.random.default_rng(5).uniform(size=(256, d))
+    dev.predict_grad(Xg)
+    dtg = 1e9
+    for _ in range(5):
+        t0 = time.perf_counter()
+        dev.predict_grad(Xg)
+        dtg = min(dtg, time.perf_counter() - t0)
+    dev.predict(Xg[:1], return_std=True)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        dev.predict(Xg[:1], return_std=True)
+    dt1 = (time.perf_counter() - t0) / 50
+    out["grad_batch"] = {"n_train": N, "dim": d, "points_per_call": 256,
+                         "ms_per_call": max_over_ranks(dtg) * 1e3,
+                         "what": "mean, std, d mean/dx, d std/dx per point, host to host"}
+    out["latency"] = {"n_train": N, "dim": d, "what": "predict(1 point, return_std) host to host",
+                      "us_per_call": max_over_ranks(dt1) * 1e6}
     # config B (and its Matern-5/2 repeat): N_train = 1000, d = 8, 10^6 candidates, mean+std+acq
     for kind in ("rbf", "matern25"):
         Nb, db, Mb = 1000, 8, 1_000_000

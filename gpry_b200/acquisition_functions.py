@@ -50,15 +50,20 @@ class LogExp:
         X = np.atleast_2d(np.asarray(X, dtype=float))
         noise_var = self.noise_var(gp)
         if eval_gradient:   # acquisition_functions.py:966-969, 993-1007 (one point)
-            mu, std, mu_grad, std_grad = gp.predict(X, return_std=True, return_mean_grad=True,
-                                                    return_std_grad=True)
+            if X.shape[0] > 1:    # many points in one device pass (the ndim > 1 branch below)
+                mu, std, mu_grad, std_grad = gp.predict_grad_batch(X)
+            else:
+                mu, std, mu_grad, std_grad = gp.predict(
+                    X, return_std=True, return_mean_grad=True, return_std_grad=True)
             var = std ** 2 - noise_var ** 2.
             mask = (var > 0) & np.isfinite(mu)
             values = np.where(mask, self.f(mu, std, gp.y_max, noise_var, self.zeta), -np.inf)
             if np.array(std_grad).ndim > 1:
                 grad = np.zeros_like(std_grad)
                 if np.any(mask):
-                    grad[mask] = np.array(std_grad)[mask] / (std[mask] - noise_var) \
+                    # (the reference's many-point branch, :996-1001, is unreachable there
+                    # and lacks this broadcast over the dimensions)
+                    grad[mask] = np.array(std_grad)[mask] / (std[mask] - noise_var)[:, None] \
                         + 2 * self.zeta * np.array(mu_grad)[mask]
                 if np.any(~mask):
                     grad[~mask] = np.inf
@@ -67,11 +72,8 @@ class LogExp:
             else:
                 grad = np.ones_like(std_grad) * np.inf
             return values, grad
-        if gp.infinities_classifier is None and gp.trust_bounds is None:
-            mu, std, values = gp.predict_logexp(X, self.zeta, noise_var)
-        else:  # masks are host-side: take mean/std through predict, then f on the host
-            mu, std = gp.predict(X, return_std=True)
-            values = self.f(mu, std, gp.y_max, noise_var, self.zeta)
+        # one fused device pass; classifier / trust-region rows come back with a non-finite mean
+        mu, std, values = gp.predict_logexp(X, self.zeta, noise_var)
         var = std ** 2 - noise_var ** 2.
         mask = (var > 0) & np.isfinite(mu)
         values = np.where(mask, values, -np.inf)

@@ -173,6 +173,8 @@ int gpry_state_destroy(gpry_state* st) {
     for (int b = 0; b < 2; b++) { st->tk_keys[b].release(); st->tk_idx[b].release(); }
     st->tmp.release(); st->small.release(); st->Vrm.release(); st->trust.release();
     st->pc_U.release(); st->pc_Ks.release(); st->pc_UT.release(); st->pc_G.release();
+    st->VTrm.release(); st->gr_out.release(); st->clf_dec.release();
+    if (st->clf) gpry_state_destroy(st->clf);
     st->f_K.release(); st->f_VT.release(); st->f_W.release(); st->f_TT.release();
     st->f_Winv.release(); st->f_misc.release(); st->f_prob.release();
     delete st;
@@ -184,7 +186,8 @@ int gpry_state_upload(gpry_state* st, int kind, int N, int d, const double* X_tr
                       const double* x_min, const double* x_width, double y_mean, double y_std,
                       double clip_hi) {
   return guarded([&] {
-    GPRY_CHECK_ARG(st && X_train_t && alpha_ && V && ell, "NULL argument");
+    GPRY_CHECK_ARG(st && X_train_t && alpha_ && ell, "NULL argument");
+    st->clf_on = false;
     upload_model(st, kind, N, d, X_train_t, alpha_, V, nullptr, nullptr, 0, nullptr, c, ell, x_min,
                  x_width, y_mean, y_std, clip_hi);
   });
@@ -197,6 +200,7 @@ int gpry_state_adopt_factorization(gpry_state* st, double c, const double* ell,
     GPRY_CHECK_ARG(st && ell, "NULL argument");
     if (!st->f_valid)
       throw GpryError{GPRY_ERR_STATE, "no device-resident factorization to adopt"};
+    st->clf_on = false;
     const int N = st->f_N, d = st->f_d;
     const int Np = round_up(N, TILE_ROWS);
     std::vector<double> Xt((size_t)N * d);
@@ -230,6 +234,67 @@ int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const doub
   });
 }
 
+int gpry_set_mask_value(gpry_state* st, double value) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    st->trust_value = value;
+  });
+}
+
+int gpry_set_classifier(gpry_state* st, int n_sv, int d, const double* sv, const double* dual_coef,
+                        double intercept, double gamma) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    if (!sv || !dual_coef) {
+      st->clf_on = false;
+      return;
+    }
+    if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "upload the model before its classifier"};
+    GPRY_CHECK_ARG(n_sv >= 1 && d == st->d, "classifier: need n_sv >= 1 and the model's d");
+    GPRY_CHECK_ARG(gamma > 0.0, "classifier: gamma must be > 0");
+    if (!st->clf) {
+      st->clf = new gpry_state();
+      st->clf->device = st->device;
+      st->clf->n_sm = st->n_sm;
+    }
+    // exp(-gamma r^2) = exp(-r^2 / (2 ell^2)) with ell = 1 / sqrt(2 gamma); same (min, width)
+    // transform as the model, decision = 1 * sum_i coef_i k_i + intercept, never clipped
+    std::vector<double> prm(3 * MAX_DIM);
+    GPRY_CUDA(cudaSetDevice(st->device));
+    GPRY_CUDA(cudaMemcpy(prm.data(), st->prm_dev.p, 3 * MAX_DIM * 8, cudaMemcpyDeviceToHost));
+    std::vector<double> ell(d, 1.0 / sqrt(2.0 * gamma));
+    upload_model(st->clf, GPRY_KERNEL_RBF, n_sv, d, sv, dual_coef, nullptr, nullptr, nullptr, 0,
+                 nullptr, 1.0, ell.data(), prm.data(), prm.data() + MAX_DIM, intercept, 1.0,
+                 INFINITY);
+    st->clf_on = true;
+  });
+}
+
+int gpry_classify(gpry_state* st, const double* X, int64_t M, int where, double* out_decision,
+                  void* stream) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    if (!st->clf_on) throw GpryError{GPRY_ERR_STATE, "no classifier set on this state"};
+    GPRY_CHECK_ARG(M >= 0, "M < 0");
+    if (M == 0) return;
+    GPRY_CHECK_ARG(X != nullptr && out_decision != nullptr, "NULL argument");
+    GPRY_CUDA(cudaSetDevice(st->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool x_dev = where & GPRY_X_ON_DEVICE, o_dev = where & GPRY_OUT_ON_DEVICE;
+    const double* dX = stage_in(st, X, (size_t)M * st->d, x_dev, st->Xdev, s);
+    double* dd = out_decision;
+    if (!o_dev) {
+      st->clf_dec.reserve((size_t)M);
+      dd = st->clf_dec.p;
+    }
+    predict_pipeline(st->clf, dX, M, true, false, false, 0, 0, 0, dd, nullptr, nullptr, s);
+    if (!o_dev) {
+      GPRY_CUDA(cudaMemcpyAsync(out_decision, dd, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
+      GPRY_CUDA(cudaStreamSynchronize(s));
+    }
+  });
+}
+
 int gpry_state_info(const gpry_state* st, int* N, int* d, int* kind) {
   if (!st || !st->loaded) {
     set_last_error("no model uploaded into this state");
@@ -244,7 +309,7 @@ int gpry_state_info(const gpry_state* st, int* N, int* d, int* kind) {
 static void predict_common(gpry_state* st, const double* X, int64_t M, bool want_mean,
                            bool want_std, bool want_acq, double zeta, double sigma_n, double y_max,
                            int where, double* out_mean, double* out_std, double* out_acq,
-                           cudaStream_t s, bool trust = false) {
+                           cudaStream_t s) {
   GPRY_CHECK_ARG(st != nullptr, "state is NULL");
   if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
   GPRY_CHECK_ARG(M >= 0, "M < 0");
@@ -266,7 +331,8 @@ static void predict_common(gpry_state* st, const double* X, int64_t M, bool want
   const double* dX = nullptr;
   run_pipeline_blocks(st, X, M, x_dev, need_var, da != nullptr, zeta, sigma_n, y_max, dm, ds, da,
                       &dX, s);
-  if (trust) apply_trust_region(st, dX, M, dm, s);
+  apply_classifier(st, dX, M, dm, ds, da, s);
+  apply_trust_region(st, dX, M, dm, da, s);
   if (!o_dev) {
     TimedScope ts(st, s, T_D2H, 0);
     if (dm) GPRY_CUDA(cudaMemcpyAsync(out_mean, dm, M * 8, cudaMemcpyDeviceToHost, s));
@@ -281,7 +347,7 @@ int gpry_predict(gpry_state* st, const double* X, int64_t M, int what, int where
                  double* out_mean, double* out_std, void* stream) {
   return guarded([&] {
     predict_common(st, X, M, what & GPRY_WANT_MEAN, what & GPRY_WANT_STD, false, 0, 0, 0, where,
-                   out_mean, out_std, nullptr, (cudaStream_t)stream, true);
+                   out_mean, out_std, nullptr, (cudaStream_t)stream);
   });
 }
 
@@ -314,6 +380,8 @@ int gpry_predict_logexp_topk(gpry_state* st, const double* X, int64_t M, double 
     const double* dX = nullptr;
     run_pipeline_blocks(st, X, M, x_dev, true, true, zeta, sigma_n, y_max, st->o_mean.p,
                         st->o_std.p, st->o_acq.p, &dX, s);
+    apply_classifier(st, dX, M, st->o_mean.p, st->o_std.p, st->o_acq.p, s);
+    apply_trust_region(st, dX, M, st->o_mean.p, st->o_acq.p, s);
     double* d_keys;
     int64_t* d_idx;
     int64_t n = topk_device(st, st->o_acq.p, M, Kp, idx_offset, &d_keys, &d_idx, s);
@@ -370,6 +438,14 @@ int gpry_mean_grad(gpry_state* st, const double* x, double* out_grad) {
   });
 }
 
+int gpry_predict_grad(gpry_state* st, const double* X, int M, double* out_mean, double* out_std,
+                      double* out_grad_mean, double* out_grad_std) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    predict_grad_device(st, X, M, out_mean, out_std, out_grad_mean, out_grad_std);
+  });
+}
+
 int gpry_std_grad(gpry_state* st, const double* x, double* out_grad, double* out_std) {
   return guarded([&] {
     GPRY_CHECK_ARG(st && x && out_grad, "NULL argument");
@@ -422,6 +498,13 @@ int gpry_factorize(gpry_state* st, int kind, int N, int d, const double* X_train
     GPRY_CHECK_ARG(st && X_train_t && noise2 && y_t && theta && info, "NULL argument");
     factorize_device(st, kind, N, d, X_train_t, noise2, y_t, theta, out_L, out_V, out_alpha,
                      out_logdet_half, info, keep_on_device != 0);
+  });
+}
+
+int gpry_factor_download(gpry_state* st, double* out_L, double* out_V) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    factor_download_device(st, out_L, out_V);
   });
 }
 

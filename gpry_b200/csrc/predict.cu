@@ -623,13 +623,13 @@ void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_
     Vsrc = VT_dev_rowmajor;
     transposed = 1;
   }
-  GPRY_CHECK_ARG(Vsrc != nullptr, "no V given");
-  int64_t total = vtile_count(st->nJ) * TILE_DOUBLES;
-  st->Vt.reserve((size_t)total);
-  pack_v_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Vsrc, N, ldV, transposed, st->nJ,
-                                                               st->Vt.p);
-  GPRY_CUDA(cudaGetLastError());
-  {
+  st->has_V = Vsrc != nullptr;     // mean-only states (the classifier's decision function)
+  if (st->has_V) {
+    int64_t total = vtile_count(st->nJ) * TILE_DOUBLES;
+    st->Vt.reserve((size_t)total);
+    pack_v_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Vsrc, N, ldV, transposed, st->nJ,
+                                                                 st->Vt.p);
+    GPRY_CUDA(cudaGetLastError());
     int64_t tot = (int64_t)st->Npad * st->Npad;
     st->Vrm.reserve((size_t)tot);
     pad_v_rowmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(Vsrc, N, ldV, transposed,
@@ -637,6 +637,7 @@ void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_
     GPRY_CUDA(cudaGetLastError());
   }
   GPRY_CUDA(cudaStreamSynchronize(s));
+  st->vtrm_valid = false;
   st->loaded = true;
 }
 
@@ -854,7 +855,7 @@ static void predict_small(gpry_state* st, const double* dX, int M, bool want_var
 // mean[i] = value for candidates outside [lo, hi] (tools.py:263-287 is_in_bounds, gpr.py:1201)
 __global__ void trust_mask_kernel(const double* __restrict__ X, int64_t M, int d,
                                   const double* __restrict__ lohi, double value,
-                                  double* __restrict__ mean) {
+                                  double* __restrict__ mean, double* __restrict__ acq) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   bool inside = true;
@@ -862,15 +863,43 @@ __global__ void trust_mask_kernel(const double* __restrict__ X, int64_t M, int d
     double x = X[i * d + k];
     inside = inside && (x >= lohi[k]) && (x <= lohi[MAX_DIM + k]);
   }
-  if (!inside) mean[i] = value;
+  if (!inside) {
+    if (mean) mean[i] = value;
+    if (acq) acq[i] = -INFINITY;   // LogExp of a non-finite mean (acquisition_functions.py:983-992)
+  }
+}
+
+// rows the classifier calls infinite (decision <= 0): mean = value, std = 0, acq = -inf
+// (gpr.py:1145, 1172, 1229-1231; acquisition_functions.py:983-992)
+__global__ void classifier_mask_kernel(const double* __restrict__ dec, int64_t M, double value,
+                                       double* __restrict__ mean, double* __restrict__ sd,
+                                       double* __restrict__ acq) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M || dec[i] > 0.0) return;
+  if (mean) mean[i] = value;
+  if (sd) sd[i] = 0.0;
+  if (acq) acq[i] = -INFINITY;
+}
+
+// decision values of the classifier for the candidates dX (device) -> st->clf_dec, then mask
+void apply_classifier(gpry_state* st, const double* dX, int64_t M, double* d_mean, double* d_std,
+                      double* d_acq, cudaStream_t s) {
+  if (!st->clf_on || M <= 0) return;
+  st->clf_dec.reserve((size_t)M);
+  predict_pipeline(st->clf, dX, M, true, false, false, 0, 0, 0, st->clf_dec.p, nullptr, nullptr, s);
+  TimedScope ts(st, s, T_FINISH);
+  classifier_mask_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(st->clf_dec.p, M,
+                                                                    st->trust_value, d_mean,
+                                                                    d_std, d_acq);
+  GPRY_CUDA(cudaGetLastError());
 }
 
 void apply_trust_region(gpry_state* st, const double* dX, int64_t M, double* d_mean,
-                        cudaStream_t s) {
-  if (!st->trust_on || !d_mean || M <= 0) return;
+                        double* d_acq, cudaStream_t s) {
+  if (!st->trust_on || (!d_mean && !d_acq) || M <= 0) return;
   TimedScope ts(st, s, T_FINISH);
   trust_mask_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(dX, M, st->d, st->trust.p,
-                                                               st->trust_value, d_mean);
+                                                               st->trust_value, d_mean, d_acq);
   GPRY_CUDA(cudaGetLastError());
 }
 
@@ -879,6 +908,8 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
                       double* d_std, double* d_acq, cudaStream_t s) {
   if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
   if (M <= 0) return;
+  if (want_var && !st->has_V)
+    throw GpryError{GPRY_ERR_STATE, "this state was uploaded without V: mean only"};
   GPRY_CUDA(cudaSetDevice(st->device));
   if (M <= SMALL_M_MAX) {   // latency path, SMALL_M candidates per pass over V
     for (int m0 = 0; m0 < (int)M; m0 += SMALL_M)
@@ -1077,6 +1108,7 @@ static void launch_kcross(int kind, const double* A, int nA, int rowsA_pad, cons
 void posterior_cov_device(gpry_state* st, const double* dX, int Ka, double* d_out,
                           cudaStream_t s) {
   if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+  if (!st->has_V) throw GpryError{GPRY_ERR_STATE, "this state was uploaded without V"};
   GPRY_CHECK_ARG(Ka >= 1 && Ka <= 8192, "posterior covariance: 1 <= Ka <= 8192");
   GPRY_CUDA(cudaSetDevice(st->device));
   const int Kap = round_up(Ka, TILE_ROWS), Np = st->Npad, DP = st->DP, d = st->d;
@@ -1269,6 +1301,7 @@ __global__ void scale_vec_kernel(double* __restrict__ v, int n, const double* __
 
 void std_grad_device(gpry_state* st, const double* x_host, double* out_grad, double* out_std) {
   if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+  if (!st->has_V) throw GpryError{GPRY_ERR_STATE, "this state was uploaded without V"};
   GPRY_CUDA(cudaSetDevice(st->device));
   const int d = st->d, N = st->N, Np = st->Npad, DP = st->DP;
   cudaStream_t s = 0;
@@ -1323,6 +1356,181 @@ void std_grad_device(gpry_state* st, const double* x_host, double* out_grad, dou
   GPRY_CUDA(cudaGetLastError());
   GPRY_CUDA(cudaMemcpyAsync(out_grad, d_out, d * 8, cudaMemcpyDeviceToHost, s));
   if (out_std) GPRY_CUDA(cudaMemcpyAsync(out_std, d_scale + 1, 8, cudaMemcpyDeviceToHost, s));
+  GPRY_CUDA(cudaStreamSynchronize(s));
+}
+
+// ---------------------------------------------------------------------------------------
+// Batched gradients (the acquisition optimiser's many starts in lock-step).
+// Per candidate m the same quantities as gpry_mean_grad / gpry_std_grad (gpr.py:1236-1261):
+//   grad_mean[m] = y_std * sum_j alpha_j dk*_mj/dx_
+//   grad_std[m]  = -(y_std^2 / sqrt(var_m)) * sum_j z_mj dk*_mj/dx_,  z_m = V^T (V k*_m)
+// K* (M x N) comes from kcross_kernel, W = K* V^T and Z = W V from the DMMA GEMM of train.cu
+// (Z needs V^T row major: transposed lazily once per upload), the contraction with dk*/dx_ is
+// one CTA per (dimension, candidate); dk*/dx_ (M x N x d) is never materialised.
+// ---------------------------------------------------------------------------------------
+__global__ void transpose_sq_kernel(const double* __restrict__ in, int n, double* __restrict__ out) {
+  __shared__ double t[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) t[r][threadIdx.x] = in[(size_t)(by + r) * n + bx + threadIdx.x];
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) out[(size_t)(bx + r) * n + by + threadIdx.x] = t[threadIdx.x][r];
+}
+
+// scale[2m] = var > 0 ? -(y_std^2)/sqrt(var) : 0,  scale[2m+1] = var (normalised), var = c - |W_m|^2
+__global__ void __launch_bounds__(256)
+grad_scale_batch_kernel(const double* __restrict__ W, int ldw, int N, double c, double y_std,
+                        double* __restrict__ scale) {
+  __shared__ double r[256];
+  const double* w = W + (size_t)blockIdx.x * ldw;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) s = fma(w[i], w[i], s);
+  r[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) r[threadIdx.x] += r[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double var = c - r[0];
+    scale[2 * blockIdx.x] = var > 0.0 ? -(y_std * y_std) / sqrt(var) : 0.0;
+    scale[2 * blockIdx.x + 1] = var;
+  }
+}
+
+// grid (d, M): block (k, m) reduces dimension k of candidate m over the training points
+template <int KIND>
+__global__ void __launch_bounds__(256)
+grad_batch_kernel(const double* __restrict__ Xt, const double* __restrict__ alpha,
+                  const double* __restrict__ Z, int ldz, int N, int d,
+                  const double* __restrict__ X, const double* __restrict__ prm, double c,
+                  double y_std, const double* __restrict__ scale, double* __restrict__ gmean,
+                  double* __restrict__ gstd) {
+  __shared__ double xt[MAX_DIM];
+  __shared__ double inv_unused;
+  __shared__ double red[2][256];
+  (void)inv_unused;
+  const int k = blockIdx.x, m = blockIdx.y;
+  const double* ell = prm + 2 * MAX_DIM;
+  for (int q = threadIdx.x; q < d; q += 256)
+    xt[q] = (X[(size_t)m * d + q] - prm[q]) / prm[MAX_DIM + q];
+  __syncthreads();
+  const double* z = Z ? Z + (size_t)m * ldz : nullptr;
+  double sm = 0.0, ss = 0.0;
+  for (int j = threadIdx.x; j < N; j += 256) {
+    double r2 = 0.0, dk = 0.0;
+    for (int q = 0; q < d; q++) {
+      double diff = (xt[q] - Xt[(size_t)j * d + q]) / ell[q];
+      r2 = fma(diff, diff, r2);
+      if (q == k) dk = diff;
+    }
+    double g;
+    if (KIND == GPRY_KERNEL_RBF) {
+      g = (-exp(-0.5 * r2) * dk) / ell[k];
+    } else if (KIND == GPRY_KERNEL_MATERN15) {
+      double dist = sqrt(r2);
+      double s3d = 1.7320508075688772 * dist;
+      double by = dist != 0.0 ? 1.7320508075688772 / dist : 0.0;
+      double f_grad = (dk / ell[k]) * by;
+      g = exp(-s3d) * f_grad * (1.0 - (1.0 + s3d));
+    } else {
+      double dist = sqrt(r2);
+      double s5d = 2.23606797749979 * dist;
+      double f = (5.0 / 3.0) * r2 + s5d + 1.0;
+      double inv = dist != 0.0 ? 2.23606797749979 * (1.0 / dist) : 0.0;
+      double dl = dk / ell[k];
+      double f1g = inv * dl, f2g = (10.0 / 3.0) * dl;
+      double gg = exp(-s5d);
+      g = f * (-gg * f1g) + gg * (f1g + f2g);
+    }
+    const double cg = c * g;
+    sm = fma(cg, alpha[j], sm);
+    if (z) ss = fma(cg, z[j], ss);
+  }
+  red[0][threadIdx.x] = sm;
+  red[1][threadIdx.x] = ss;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + o];
+      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (gmean) gmean[(size_t)m * d + k] = red[0][0] * y_std;
+    if (gstd) gstd[(size_t)m * d + k] = red[1][0] * scale[2 * m];
+  }
+}
+
+void predict_grad_device(gpry_state* st, const double* hX, int M, double* h_mean, double* h_std,
+                         double* h_gmean, double* h_gstd) {
+  if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+  GPRY_CHECK_ARG(M >= 1 && M <= 8192, "batched gradients: 1 <= M <= 8192");
+  if (h_gstd && !st->has_V) throw GpryError{GPRY_ERR_STATE, "this state was uploaded without V"};
+  GPRY_CHECK_ARG(hX != nullptr, "X is NULL");
+  GPRY_CUDA(cudaSetDevice(st->device));
+  const int d = st->d, N = st->N, Np = st->Npad, DP = st->DP;
+  const int Mp = round_up(M, TILE_ROWS);
+  cudaStream_t s = 0;
+  st->Xdev.reserve((size_t)M * d);
+  GPRY_CUDA(cudaMemcpyAsync(st->Xdev.p, hX, (size_t)M * d * 8, cudaMemcpyHostToDevice, s));
+  double *dm = nullptr, *ds = nullptr;
+  if (h_mean) { st->o_mean.reserve(M); dm = st->o_mean.p; }
+  if (h_std) { st->o_std.reserve(M); ds = st->o_std.p; }
+  if (dm || ds)
+    predict_pipeline(st, st->Xdev.p, M, dm != nullptr, ds != nullptr, false, 0, 0, 0, dm, ds, nullptr, s);
+  st->gr_out.reserve((size_t)2 * M * d + 2 * (size_t)Mp);
+  double* d_gm = st->gr_out.p;
+  double* d_gs = d_gm + (size_t)M * d;
+  double* d_scale = d_gs + (size_t)M * d;
+  const double* Z = nullptr;
+  if (h_gstd) {
+    if (!st->vtrm_valid) {
+      st->VTrm.reserve((size_t)Np * Np);
+      transpose_sq_kernel<<<dim3(Np / 32, Np / 32), dim3(32, 8), 0, s>>>(st->Vrm.p, Np, st->VTrm.p);
+      GPRY_CUDA(cudaGetLastError());
+      st->vtrm_valid = true;
+    }
+    st->pc_U.reserve((size_t)Mp * DP);
+    st->pc_Ks.reserve((size_t)Mp * Np);
+    st->pc_UT.reserve((size_t)Mp * Np);
+    scale_candidates_kernel<<<(Mp * DP + 255) / 256, 256, 0, s>>>(st->Xdev.p, M, d, Mp, DP,
+                                                                  st->prm_dev.p, st->pc_U.p);
+    GPRY_CUDA(cudaGetLastError());
+    launch_kcross(st->kind, st->pc_U.p, M, Mp, st->T.p, N, DP, st->c, Np, nullptr, st->pc_Ks.p, s);
+    // W = K* V^T  (W[m][j] = sum_k K*[m][k] V[j][k])
+    gemm_nt(st->pc_Ks.p, Np, st->Vrm.p, Np, st->pc_UT.p, Np, Mp, Np, Np, 1.0, 0, 0, 0, s);
+    grad_scale_batch_kernel<<<M, 256, 0, s>>>(st->pc_UT.p, Np, N, st->c, st->y_std, d_scale);
+    GPRY_CUDA(cudaGetLastError());
+    // Z = W V  (Z[m][i] = sum_j W[m][j] V[j][i]) -> reuses the K* buffer
+    gemm_nt(st->pc_UT.p, Np, st->VTrm.p, Np, st->pc_Ks.p, Np, Mp, Np, Np, 1.0, 0, 0, 0, s);
+    Z = st->pc_Ks.p;
+  }
+  if (h_gmean || h_gstd) {
+    dim3 grid(d, M);
+    double* gm = h_gmean ? d_gm : nullptr;
+    double* gs = h_gstd ? d_gs : nullptr;
+    switch (st->kind) {
+      case GPRY_KERNEL_RBF:
+        grad_batch_kernel<GPRY_KERNEL_RBF><<<grid, 256, 0, s>>>(
+            st->Xt.p, st->alpha.p, Z, Np, N, d, st->Xdev.p, st->prm_dev.p, st->c, st->y_std, d_scale, gm, gs);
+        break;
+      case GPRY_KERNEL_MATERN15:
+        grad_batch_kernel<GPRY_KERNEL_MATERN15><<<grid, 256, 0, s>>>(
+            st->Xt.p, st->alpha.p, Z, Np, N, d, st->Xdev.p, st->prm_dev.p, st->c, st->y_std, d_scale, gm, gs);
+        break;
+      default:
+        grad_batch_kernel<GPRY_KERNEL_MATERN25><<<grid, 256, 0, s>>>(
+            st->Xt.p, st->alpha.p, Z, Np, N, d, st->Xdev.p, st->prm_dev.p, st->c, st->y_std, d_scale, gm, gs);
+    }
+    GPRY_CUDA(cudaGetLastError());
+  }
+  if (h_mean) GPRY_CUDA(cudaMemcpyAsync(h_mean, dm, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
+  if (h_std) GPRY_CUDA(cudaMemcpyAsync(h_std, ds, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
+  if (h_gmean)
+    GPRY_CUDA(cudaMemcpyAsync(h_gmean, d_gm, (size_t)M * d * 8, cudaMemcpyDeviceToHost, s));
+  if (h_gstd)
+    GPRY_CUDA(cudaMemcpyAsync(h_gstd, d_gs, (size_t)M * d * 8, cudaMemcpyDeviceToHost, s));
   GPRY_CUDA(cudaStreamSynchronize(s));
 }
 

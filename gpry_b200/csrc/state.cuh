@@ -70,6 +70,10 @@ struct gpry_state {
   int nKT = 0;    // k-tiles per candidate tile (Npad / 16)
   double c = 1.0, y_mean = 0.0, y_std = 1.0, clip_hi = 0.0;
   // optional trust region applied to the mean on the device (gpr.py:1104-1109, 1200-1201)
+  bool has_V = true;                     // false: mean-only state (classifier)
+  gpry_state* clf = nullptr;             // infinities classifier: a mean-only sub-state whose
+  bool clf_on = false;                   //   'mean' is the SVC decision function (svm.py:308-346)
+  gpry::DevBuf<double> clf_dec;          // decision values of the current call
   bool trust_on = false;
   double trust_value = 0.0;
   gpry::DevBuf<double> trust;            // [2][MAX_DIM] lower, upper (un-transformed)
@@ -81,6 +85,8 @@ struct gpry_state {
   gpry::DevBuf<double> Vt;               // tiled lower block triangle of V = L^-1
   gpry::DevBuf<double> Vrm;              // [Npad][Npad] row-major V, zero padded (posterior cov)
   gpry::DevBuf<double> pc_U, pc_Ks, pc_UT, pc_G;   // posterior-covariance scratch
+  gpry::DevBuf<double> VTrm, gr_out;     // [Npad][Npad] row-major V^T (lazy), batched-gradient outputs
+  bool vtrm_valid = false;
 
   // scratch (grown on demand, reused across calls)
   gpry::DevBuf<double> Ks;               // [chunk_tiles][nKT] K* tiles
@@ -130,8 +136,12 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
                       bool want_var, bool want_acq, double zeta, double sigma_n, double y_max,
                       double* d_mean, double* d_std, double* d_acq, cudaStream_t s);
 void mean_grad_device(gpry_state* st, const double* x_host, double* out_host);
+void predict_grad_device(gpry_state* st, const double* hX, int M, double* h_mean, double* h_std,
+                         double* h_gmean, double* h_gstd);
+void apply_classifier(gpry_state* st, const double* dX, int64_t M, double* d_mean, double* d_std,
+                      double* d_acq, cudaStream_t s);
 void apply_trust_region(gpry_state* st, const double* dX, int64_t M, double* d_mean,
-                        cudaStream_t s);
+                        double* d_acq, cudaStream_t s);
 void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                   const double* alpha_, const double* V_host, const double* V_dev_rowmajor,
                   const double* VT_dev_rowmajor, int ldV, const double* alpha_dev, double c,
@@ -155,6 +165,7 @@ void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_tr
                       const double* noise2, const double* y_t, const double* theta,
                       double* out_L, double* out_V, double* out_alpha, double* out_logdet_half,
                       int* info, bool keep);
+void factor_download_device(gpry_state* st, double* out_L, double* out_V);
 void lml_batched_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                         const double* noise2, const double* y_t, const double* thetas, int B,
                         double* out_lml, double* out_grad, int* out_info);

@@ -916,6 +916,27 @@ void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_tr
   }
 }
 
+// L and / or V of the factorisation kept resident by factorize_device(keep = true)
+void factor_download_device(gpry_state* st, double* out_L, double* out_V) {
+  if (!st->f_valid) throw GpryError{GPRY_ERR_STATE, "no device-resident factorization"};
+  GPRY_CUDA(cudaSetDevice(st->device));
+  cudaStream_t s = 0;
+  const int N = st->f_N, Np = round_up(N, NB);
+  const int64_t tot = (int64_t)N * N;
+  st->tmp.reserve((size_t)tot);
+  if (out_L) {
+    extract_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(st->f_K.p, Np, N, 0, st->tmp.p);
+    GPRY_CUDA(cudaGetLastError());
+    GPRY_CUDA(cudaMemcpyAsync(out_L, st->tmp.p, tot * 8, cudaMemcpyDeviceToHost, s));
+  }
+  if (out_V) {
+    extract_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(st->f_VT.p, Np, N, 1, st->tmp.p);
+    GPRY_CUDA(cudaGetLastError());
+    GPRY_CUDA(cudaMemcpyAsync(out_V, st->tmp.p, tot * 8, cudaMemcpyDeviceToHost, s));
+  }
+  GPRY_CUDA(cudaStreamSynchronize(s));
+}
+
 void lml_batched_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                         const double* noise2, const double* y_t, const double* thetas, int B,
                         double* out_lml, double* out_grad, int* out_info) {

@@ -74,7 +74,7 @@ class DeviceGP:
         X_train_ = as_f64(X_train_)
         N, d = X_train_.shape
         alpha_ = as_f64(alpha_, (N,))
-        V_ = as_f64(V_, (N, N))
+        V_ = None if V_ is None else as_f64(V_, (N, N))     # None: mean-only model
         ell = as_f64(np.broadcast_to(ell, (d,)))
         x_min = None if x_min is None else as_f64(x_min, (d,))
         x_width = None if x_width is None else as_f64(x_width, (d,))
@@ -94,8 +94,38 @@ class DeviceGP:
             float(y_std), float(clip_hi)))
         self.N, self.d, self.kind = self._f_N, d, self._f_kind
 
+    def set_mask_value(self, value):
+        """The value masked rows get for the mean (``minus_inf_value``)."""
+        check(self._lib.gpry_set_mask_value(self._h, float(value)))
+
+    def set_classifier(self, spec=None):
+        """Device-side infinities classifier: ``spec = (support vectors (n_sv, d) in the
+        transformed space, dual_coef (n_sv,), intercept, gamma)`` or None to clear.  Cleared
+        by every ``upload`` / ``adopt_factorization``."""
+        if spec is None:
+            check(self._lib.gpry_set_classifier(self._h, 0, 0, None, None, 0.0, 1.0))
+            return
+        sv, coef, intercept, gamma = spec
+        sv = as_f64(sv)
+        coef = as_f64(coef, (sv.shape[0],))
+        check(self._lib.gpry_set_classifier(self._h, sv.shape[0], sv.shape[1], ptr(sv), ptr(coef),
+                                            float(intercept), float(gamma)))
+
+    def classify(self, X, stream=None):
+        """Decision values of the device-side classifier (> 0: finite)."""
+        X, M, where = self._prep_X(X)
+        if where & _lib.X_ON_DEVICE:
+            import torch
+            out = torch.empty(M, dtype=torch.float64, device=X.device)
+            where |= _lib.OUT_ON_DEVICE
+        else:
+            out = np.empty(M)
+        check(self._lib.gpry_classify(self._h, ptr(X), M, where, ptr(out), _stream_ptr(stream)))
+        return out
+
     def set_trust_region(self, bounds=None, value=-np.inf):
-        """Device-side trust region for ``predict``'s mean: (d, 2) bounds or None to clear."""
+        """Device-side trust region (mean, and acq in the acquisition calls): (d, 2) bounds or
+        None to clear."""
         if bounds is None:
             check(self._lib.gpry_set_trust_region(self._h, 0, None, None, 0.0))
             return
@@ -213,6 +243,20 @@ class DeviceGP:
         check(self._lib.gpry_std_grad(self._h, ptr(x), ptr(out), C.byref(std)))
         return out, std.value
 
+    def predict_grad(self, X, return_std_grad=True):
+        """Batched mean, std, d mean/dx_ and d std/dx_ for the rows of a host array X
+        (M <= 8192); the per-row conventions of ``predict``, ``mean_grad`` and ``std_grad``."""
+        X = as_f64(X)
+        if X.ndim != 2 or X.shape[1] != self.d:
+            raise ValueError(f"X must have shape (M, {self.d})")
+        M = X.shape[0]
+        mean, std = np.empty(M), np.empty(M)
+        gm = np.empty((M, self.d))
+        gs = np.empty((M, self.d)) if return_std_grad else None
+        check(self._lib.gpry_predict_grad(self._h, ptr(X), M, ptr(mean), ptr(std), ptr(gm),
+                                          ptr(gs) if gs is not None else None))
+        return mean, std, gm, gs
+
     def posterior_cov(self, X, stream=None):
         """Posterior covariance (normalised units, no noise) among the rows of X (Ka <= 8192)."""
         X, Ka, where = self._prep_X(X)
@@ -263,6 +307,14 @@ class DeviceGP:
         if keep_on_device and info.value == 0:
             self._f_N, self._f_d, self._f_kind = N, d, kind
         return L, V, alpha_, logdet_half.value, info.value
+
+    def factor_download(self, want_L=True, want_V=True):
+        """(L_, V_) of the factorisation kept on the device by ``factorize(keep_on_device=True)``."""
+        N = self._f_N
+        L = np.empty((N, N)) if want_L else None
+        V = np.empty((N, N)) if want_V else None
+        check(self._lib.gpry_factor_download(self._h, ptr(L), ptr(V)))
+        return L, V
 
     def lml_batched(self, kind, X_train_, noise2, y_train_, thetas, eval_gradient=True):
         X_train_ = as_f64(X_train_)

@@ -28,6 +28,7 @@ from functools import partial
 import numpy as np
 
 from .acquisition_functions import LogExp
+from .gpr import is_in_bounds
 
 
 class _RefitConditioner:
@@ -279,9 +280,11 @@ class NORA:
     """Batch acquisition from a ranked MC pool (gp_acquisition.py:525-1191).
 
     The MC sample of the GP mean normally comes from an external nested sampler (PolyChord /
-    UltraNest / nessai: out of scope here); it can be handed in through ``X_mc``, or drawn
-    with the reference's test sampler ``sampler="uniform"`` (1000 d uniform points,
-    gp_acquisition.py:676-682, 748-758).  Everything from the scoring on runs on the GPU.
+    UltraNest / nessai: out of scope here); it can be handed in through ``X_mc``, drawn with
+    the reference's test sampler ``sampler="uniform"`` (1000 d uniform points,
+    gp_acquisition.py:676-682, 748-758), or drawn from the surrogate posterior itself with
+    ``sampler="ensemble"``: the batched GPU ensemble sampler of ``gpry_b200.mc`` (``nsamples``
+    walkers, ``mc_steps`` updates).  Everything from the scoring on runs on the GPU.
 
     With ``torch.distributed`` initialised (one process per GPU) the pool is sharded by
     stride as ``mpi.step_split`` does (mpi.py:105-115), every rank scores its shard, the
@@ -290,7 +293,7 @@ class NORA:
     """
 
     def __init__(self, bounds, acq_func=None, mc_every=1, sampler="uniform", nsamples=None,
-                 kprime=256, verbose=1):
+                 kprime=256, verbose=1, mc_steps=100):
         self.bounds = np.asarray(bounds, dtype=float)
         d = self.bounds.shape[0]
         self.acq_func = acq_func if acq_func is not None else LogExp(dimension=d)
@@ -298,6 +301,7 @@ class NORA:
         self.mc_every_i = 0
         self.sampler = sampler
         self.nsamples = nsamples if nsamples is not None else 1000 * d
+        self.mc_steps = mc_steps
         self.kprime = kprime
         self.verbose = verbose
         self._X_mc = None
@@ -306,11 +310,18 @@ class NORA:
         self.last_kprime = None
 
     def do_MC_sample(self, gpr, bounds=None, rng=None):
-        if self.sampler != "uniform":
-            raise NotImplementedError("only the 'uniform' test sampler is built in; pass X_mc "
-                                      "from your nested sampler")
         b = self.bounds if bounds is None else np.asarray(bounds)
         rng = np.random.default_rng(rng) if not isinstance(rng, np.random.Generator) else rng
+        if self.sampler == "ensemble":
+            from .mc import ensemble_sample
+            res = ensemble_sample(gpr, bounds=b, n_walkers=self.nsamples + self.nsamples % 2,
+                                  n_steps=self.mc_steps, seed=int(rng.integers(2 ** 31)),
+                                  X_init="training")
+            self.last_mc = res
+            return res.X[:self.nsamples]
+        if self.sampler != "uniform":
+            raise NotImplementedError("built-in samplers: 'uniform' (the reference's test "
+                                      "sampler) and 'ensemble'; or pass X_mc from your own")
         return rng.uniform(b[:, 0], b[:, 1], size=(self.nsamples, b.shape[0]))
 
     def multi_add(self, gpr, n_points=1, bounds=None, rng=None, force_resample=False,
@@ -376,3 +387,227 @@ class NORA:
             acq_pool = acq_func(y_pool, merged.sigma[:n_points])
         self._X_already_proposed = np.concatenate([self._X_already_proposed, X_pool])
         return X_pool, y_pool, acq_pool
+
+
+def _number_times_d(value, d, varname):
+    """"5d" -> 5 * d, "d" -> d, numbers pass through (tools.py:185-240 ``get_Xnumber``)."""
+    if isinstance(value, str):
+        if "d" not in value:
+            raise ValueError(f"'{varname}' must be a number or a string like '5d', got {value!r}")
+        factor, power = value.split("d")
+        factor = float(factor) if factor else 1.0
+        power = float(power.lstrip("^")) if power else 1.0
+        return int(factor * d ** power)
+    return int(value)
+
+
+class BatchOptimizer:
+    """Acquisition by direct multi-start optimisation of the acquisition function with
+    Kriging-believer lies between the points of a batch (gp_acquisition.py:121-520).
+
+    The reference runs ``n_restarts_optimizer`` scipy L-BFGS-B one after the other, every
+    objective call being a one-point ``predict(return_std, return_mean_grad,
+    return_std_grad)`` (:316-336, 503-511), and scores the start-point proposals one by one
+    (:364-379).  Here the proposals of all restarts are scored in one device pass and the
+    restarts advance in lock-step: each round of objective calls is ONE batched
+    ``gpry_predict_grad`` (mean, std and both gradients for every active restart).  Start
+    selection, the optimiser, the choice of the best optimum, the lie and the append follow
+    the reference; with ``torch.distributed`` initialised the restarts are split over the
+    ranks as mpi.split_number_for_parallel_processes does (:454-458) and every rank returns
+    the same result.
+    """
+
+    def __init__(self, bounds, preprocessing_X=None, verbose=1, acq_func="LogExp",
+                 proposer=None, acq_optimizer="fmin_l_bfgs_b", n_restarts_optimizer="5d",
+                 n_repeats_propose=10):
+        from .proposal import Proposer, PartialProposer, CentroidsProposer
+        self.bounds_ = np.asarray(bounds, dtype=float)
+        self.n_d = self.bounds_.shape[0]
+        self.preprocessing_X = preprocessing_X
+        self.verbose = verbose
+        if isinstance(acq_func, str):
+            if acq_func.lower() != "logexp":
+                raise ValueError(f"Unknown acquisition function {acq_func!r}; 'LogExp' is built in")
+            acq_func = LogExp(dimension=self.n_d)
+        elif isinstance(acq_func, dict):
+            name, args = next(iter(acq_func.items()))
+            if name.lower() != "logexp":
+                raise ValueError(f"Unknown acquisition function {name!r}; 'LogExp' is built in")
+            acq_func = LogExp(dimension=self.n_d, **(args or {}))
+        self.acq_func = acq_func
+        if proposer is None:
+            self.proposer = PartialProposer(self.bounds_, CentroidsProposer(self.bounds_))
+        else:
+            if not isinstance(proposer, Proposer):
+                raise TypeError("'proposer' must be a Proposer instance. "
+                                f"Got {proposer} of type {type(proposer)}.")
+            self.proposer = proposer
+            self.proposer.update_bounds(self.bounds_)
+        has_gradient = getattr(self.acq_func, "hasgradient", True)
+        if acq_optimizer == "auto":
+            self.acq_optimizer = "fmin_l_bfgs_b" if has_gradient else "sampling"
+        elif isinstance(acq_optimizer, str):
+            if acq_optimizer == "fmin_l_bfgs_b" and not has_gradient:
+                raise ValueError("In order to use the 'fmin_l_bfgs_b' optimizer the acquisition "
+                                 f"function needs to be able to return gradients. Got {acq_func}")
+            if acq_optimizer not in ("fmin_l_bfgs_b", "sampling"):
+                raise ValueError("Supported internal optimizers are 'auto', 'lbfgs' or "
+                                 f"'sampling', got {acq_optimizer}")
+            self.acq_optimizer = acq_optimizer
+        else:
+            self.acq_optimizer = acq_optimizer
+        self.n_restarts_optimizer = _number_times_d(n_restarts_optimizer, self.n_d,
+                                                    "n_restarts_optimizer")
+        self.n_repeats_propose = n_repeats_propose
+
+    # ------------------------------------------------------------------ coordinates
+    def _to_opt(self, X):
+        return X if self.preprocessing_X is None else self.preprocessing_X.transform(X)
+
+    def _from_opt(self, X):
+        return X if self.preprocessing_X is None else self.preprocessing_X.inverse_transform(X)
+
+    def _opt_bounds(self, bounds):
+        if self.preprocessing_X is None:
+            return bounds
+        return self.preprocessing_X.transform_bounds(bounds)
+
+    # ------------------------------------------------------------------ objective
+    def _objective_batch(self, gpr):
+        """(-acq, -grad) for the rows of X given in the optimiser's coordinates
+        (gp_acquisition.py:316-336)."""
+        def batch(X):
+            X = self._from_opt(np.atleast_2d(np.asarray(X, dtype=float)))
+            acq, grad = self.acq_func(X, gpr, eval_gradient=True)
+            return -1 * np.atleast_1d(acq), -1 * np.atleast_2d(grad)
+        return batch
+
+    # ------------------------------------------------------------------ starting points
+    def _starting_points(self, gpr, i_restarts, bounds, rng):
+        """One start per restart index (gp_acquisition.py:346-390): index 0 starts from the
+        last in-bounds training point, the others from the best of the first
+        ``n_repeats_propose + 1`` proposals with a finite acquisition value, out of at most
+        ``10 d n_restarts_optimizer`` tries.  Returns (x0 (n, d) un-transformed, value (n,),
+        optimise (n,) bool): a restart that found no finite value is not optimised."""
+        n = len(i_restarts)
+        d = self.n_d
+        need = self.n_repeats_propose + 1
+        n_tries = 10 * d * self.n_restarts_optimizer
+        x0 = np.empty((n, d))
+        value = np.full(n, -np.inf)
+        optimise = np.ones(n, dtype=bool)
+        n_found = np.zeros(n, dtype=int)
+        tries = np.zeros(n, dtype=int)
+        proposing = np.ones(n, dtype=bool)
+        for r, i in enumerate(i_restarts):
+            if i == 0:
+                x0[r] = next(X for X in gpr.X_train[::-1] if np.all(is_in_bounds(X, bounds)))
+                proposing[r] = False
+        while True:
+            todo = [r for r in range(n)
+                    if proposing[r] and n_found[r] < need and tries[r] < n_tries]
+            if not todo:
+                break
+            per = [min(need, n_tries - tries[r]) for r in todo]
+            X = self.proposer.get_batch(int(np.sum(per)), rng=rng)
+            vals = np.atleast_1d(self.acq_func(X, gpr))
+            off = 0
+            for r, m in zip(todo, per):
+                for j in range(off, off + m):
+                    if n_found[r] == need:
+                        break
+                    tries[r] += 1
+                    if np.isfinite(vals[j]):
+                        n_found[r] += 1
+                        if n_found[r] == 1 or vals[j] > value[r]:
+                            value[r], x0[r] = vals[j], X[j]
+                    elif n_found[r] == 0:
+                        x0[r], value[r] = X[j], vals[j]   # the last draw, should none be finite
+                off += m
+        optimise[proposing & (n_found == 0)] = False
+        return x0, value, optimise
+
+    # ------------------------------------------------------------------ optimisation
+    def _optimize_all(self, gpr, x0_opt, opt_bounds):
+        batch = self._objective_batch(gpr)
+        if self.acq_optimizer == "fmin_l_bfgs_b":
+            from .lockstep import lockstep_minimize
+            return lockstep_minimize(batch, x0_opt, opt_bounds)
+        out = []
+        for x0 in x0_opt:
+            if self.acq_optimizer == "sampling":
+                def value_only(x):
+                    X = self._from_opt(np.atleast_2d(x))
+                    return -1 * float(np.atleast_1d(self.acq_func(X, gpr))[0])
+                import scipy.optimize
+                res = scipy.optimize.minimize(value_only, x0, method="Powell", bounds=opt_bounds)
+                out.append((res.x, res.fun))
+            elif callable(self.acq_optimizer):
+                def obj_func(x, eval_gradient=False):
+                    f, g = batch(np.atleast_2d(x))
+                    return (f[0], g[0]) if eval_gradient else f[0]
+                out.append(tuple(self.acq_optimizer(obj_func, x0, bounds=opt_bounds)))
+            else:
+                raise ValueError("Unknown optimizer %s." % self.acq_optimizer)
+        return out
+
+    def optimize_acquisition_function(self, gpr, i, bounds=None, rng=None):
+        """One restart (gp_acquisition.py:262-390) -> (x_opt in optimiser coordinates, -acq)."""
+        rng = np.random.default_rng(rng) if not isinstance(rng, np.random.Generator) else rng
+        use_bounds = self.bounds_ if bounds is None else np.asarray(bounds, dtype=float)
+        self.proposer.update(gpr)
+        self.proposer.update_bounds(use_bounds)
+        x0, value, optimise = self._starting_points(gpr, [i], use_bounds, rng)
+        if not optimise[0]:
+            return self._to_opt(x0)[0], -1 * value[0]
+        x, f = self._optimize_all(gpr, self._to_opt(x0), self._opt_bounds(use_bounds))[0]
+        return x, f
+
+    def multi_add(self, gpr, n_points=1, bounds=None, rng=None, force_resample=False):
+        """gp_acquisition.py:392-501 -> (X (n_points, d), y_lies, acq values), the same on
+        every rank."""
+        from . import parallel
+        if not (isinstance(n_points, int) and n_points > 0):
+            raise ValueError(f"n_points should be int > 0, got {n_points}")
+        rng = np.random.default_rng(rng) if not isinstance(rng, np.random.Generator) else rng
+        use_bounds = self.bounds_ if bounds is None else np.asarray(bounds, dtype=float)
+        opt_bounds = self._opt_bounds(use_bounds)
+        X_opts = np.empty((n_points, gpr.d))
+        y_lies = np.empty(n_points)
+        acq_vals = np.empty(n_points)
+        gpr_ = parallel.bcast(deepcopy(gpr) if parallel.is_main_process() else None)
+        n_per = parallel.split_number_for_parallel_processes(self.n_restarts_optimizer)
+        n_this = n_per[parallel.rank()]
+        i_first = int(sum(n_per[:parallel.rank()]))
+        for ipoint in range(n_points):
+            self.proposer.update(gpr_)
+            self.proposer.update_bounds(use_bounds)
+            proposal_X = np.empty((n_this, gpr_.d))
+            acq_X = np.empty(n_this)
+            if n_this:
+                x0, value, optimise = self._starting_points(
+                    gpr_, list(range(i_first, i_first + n_this)), use_bounds, rng)
+                x0_opt = self._to_opt(x0)
+                proposal_X[:] = x0_opt
+                acq_X[:] = -1 * value
+                run = np.flatnonzero(optimise)
+                if len(run):
+                    for r, (x, f) in zip(run, self._optimize_all(gpr_, x0_opt[run], opt_bounds)):
+                        proposal_X[r], acq_X[r] = x, f
+            if parallel.multiple_processes():
+                parts = parallel.allgather((proposal_X, acq_X))
+                proposal_X = np.concatenate([p[0] for p in parts])
+                acq_X = np.concatenate([p[1] for p in parts])
+            # gp_acquisition.py:471-497, identical on every rank (same gathered arrays)
+            max_pos = np.argmin(acq_X) if np.any(np.isfinite(acq_X)) else len(acq_X) - 1
+            X_opt = self._from_opt(np.array([proposal_X[max_pos]]))
+            acq_val = -1 * acq_X[max_pos]
+            y_lie = gpr_.predict(X_opt)
+            if ipoint < n_points - 1:
+                lie_noise_level = (np.array([np.mean(gpr_.noise_level)])
+                                   if np.iterable(gpr_.noise_level) else None)
+                gpr_.append_to_data(X_opt, y_lie, noise_level=lie_noise_level, fit_gpr=False,
+                                    fit_classifier=False)
+            X_opts[ipoint], y_lies[ipoint], acq_vals[ipoint] = X_opt[0], y_lie[0], acq_val
+        gpr.n_eval = gpr_.n_eval
+        return X_opts, y_lies, acq_vals

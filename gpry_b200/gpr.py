@@ -17,7 +17,6 @@ fitted attributes (``X_train_, y_train_, alpha, alpha_, L_, V_, kernel_`` ...) a
 arrays; the device handle lives outside the copied state and is rebuilt lazily.
 """
 import os
-import threading
 import warnings
 from copy import deepcopy
 from numbers import Number
@@ -26,6 +25,7 @@ from operator import itemgetter
 import numpy as np
 import scipy.optimize
 
+from .lockstep import lockstep_minimize
 from .device import DeviceGP, workspace
 from .kernels import ConstantKernel as C, RBF, Matern, Product
 from .preprocessing import DummyPreprocessor
@@ -120,16 +120,13 @@ class GaussianProcessRegressor:
         self.n_restarts_optimizer = n_restarts_optimizer
         self.random_state = random_state
         self.inf_threshold = inf_threshold
-        # Infinities classifier: host-side and out of scope of the B200 path; any object with
-        # the interface of gpry.svm.SVM (fit / predict / _is_finite_raw) can be plugged in.
+        # Infinities classifier (gpr.py:296-303): "SVM" = gpry_b200.svm.SVM, trained on the host
+        # like the reference's, evaluated on the device inside the predict calls.  Any other
+        # object with the interface of gpry.svm.SVM (fit / predict / _is_finite_raw) can be
+        # plugged in and is then called on the host, as in the reference.
         if isinstance(account_for_inf, str) and account_for_inf.lower() == "svm":
-            try:
-                from gpry.svm import SVM   # the reference's own classifier, if installed
-            except ImportError as excpt:
-                raise NotImplementedError(
-                    "account_for_inf='SVM' needs gpry.svm.SVM (host-side classifier, not "
-                    "part of gpry_b200); pass a classifier object or None.") from excpt
-            self.infinities_classifier = SVM(random_state=random_state)
+            from .svm import SVM
+            self.infinities_classifier = SVM(random_state=random_state, device=device)
         elif account_for_inf is False or account_for_inf is None:
             self.infinities_classifier = None
         else:
@@ -177,11 +174,15 @@ class GaussianProcessRegressor:
         self.device = default_device() if device is None else int(device)
         self._dev = None          # DeviceGP holding the predict state (never pickled)
         self._dev_dirty = True
+        self._clf_bound = None    # (id, version) of the classifier bound to the device state
+        self._clf_const = None    # True / False when the classifier answers without an SVC
+        self._factor_resident = False   # L_ / V_ live on the device only (see the properties)
 
     # ------------------------------------------------------------------ pickling / copies
-    _NOT_COPIED = ("_dev", "_dev_dirty")
+    _NOT_COPIED = ("_dev", "_dev_dirty", "_clf_bound", "_clf_const", "_factor_resident")
 
     def __getstate__(self):
+        self._materialize_factor()      # L_ / V_ may still live on the device only
         state = {k: v for k, v in self.__dict__.items() if k not in self._NOT_COPIED}
         return state
 
@@ -189,19 +190,57 @@ class GaussianProcessRegressor:
         self.__dict__.update(state)
         self._dev = None
         self._dev_dirty = True
+        self._factor_resident = False
+        self._clf_bound = None
+        self._clf_const = None
 
     def __deepcopy__(self, memo):
         """Same observable result as gpr.py:1354-1433 (a fresh instance carrying copies of
         the data and fitted attributes); the device state is rebuilt lazily by the copy."""
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
+        self._materialize_factor()
         for k, v in self.__dict__.items():
             if k in self._NOT_COPIED:
                 continue
             new.__dict__[k] = deepcopy(v, memo)
         new._dev = None
         new._dev_dirty = True
+        new._clf_bound = None
+        new._clf_const = None
+        new._factor_resident = False
         return new
+
+    # ------------------------------------------------------------------ lazy L_ / V_
+    # gpr.py:1456-1457 keeps L_ and V_ = L^-1 as dense host arrays.  Here the factorisation is
+    # produced and consumed on the device (``gpry_factorize(keep_on_device)`` ->
+    # ``gpry_state_adopt_factorization``); the two N x N host copies (2 x 128 MB at N = 4000,
+    # most of the cost of a model update) are fetched only when something reads the
+    # attributes: a pickle, a deep copy, a plot, a test.
+    def _materialize_factor(self):
+        if self.__dict__.get("_factor_resident") and self.__dict__.get("_V") is None:
+            self._L, self._V = self._dev.factor_download()
+            self._factor_resident = False
+
+    @property
+    def L_(self):
+        self._materialize_factor()
+        return self.__dict__.get("_L")
+
+    @L_.setter
+    def L_(self, value):
+        self._L = value
+        self._factor_resident = False
+
+    @property
+    def V_(self):
+        self._materialize_factor()
+        return self.__dict__.get("_V")
+
+    @V_.setter
+    def V_(self, value):
+        self._V = value
+        self._factor_resident = False
 
     # ------------------------------------------------------------------ properties
     @property
@@ -514,76 +553,12 @@ class GaussianProcessRegressor:
             raise ValueError("Unknown optimizer %s." % self.optimizer)
 
     def _lockstep_optimization(self, theta_initials, bounds):
-        """Runs one scipy L-BFGS-B per restart in its own thread; their objective calls meet
-        at a barrier and are evaluated together by ``log_marginal_likelihood_batch``."""
-        n = len(theta_initials)
-        cond = threading.Condition()
-        pending = {}          # restart -> theta waiting for evaluation
-        results = {}          # restart -> (f, g)
-        active = set(range(n))
-        optima = [None] * n
-        errors = []
-
-        def flush_locked():
-            idx = sorted(pending)
-            thetas = np.array([pending[i] for i in idx])
-            try:
-                lml, grad = self.log_marginal_likelihood_batch(thetas, eval_gradient=True)
-            except Exception as excpt:     # wake everybody up: nobody must wait forever
-                errors.append(excpt)
-                pending.clear()
-                cond.notify_all()
-                raise
-            for j, i in enumerate(idx):
-                results[i] = (-lml[j], -grad[j])
-            pending.clear()
-            cond.notify_all()
-
-        def obj(i):
-            def f(theta):
-                with cond:
-                    if errors:
-                        raise RuntimeError("another restart failed") from errors[0]
-                    pending[i] = np.array(theta, dtype=float)
-                    if len(pending) == len(active):
-                        flush_locked()
-                    else:
-                        while i not in results:
-                            if errors:
-                                raise RuntimeError("another restart failed") from errors[0]
-                            cond.wait()
-                    return results.pop(i)
-            return f
-
-        def run(i):
-            try:
-                with warnings.catch_warnings():
-                    warnings.simplefilter("ignore")
-                    res = scipy.optimize.minimize(obj(i), theta_initials[i], method="L-BFGS-B",
-                                                  jac=True, bounds=bounds)
-                optima[i] = (res.x, res.fun)
-            except Exception as excpt:
-                with cond:
-                    if not errors:
-                        errors.append(excpt)
-            finally:
-                with cond:
-                    active.discard(i)
-                    if pending and len(pending) == len(active) and not errors:
-                        try:
-                            flush_locked()
-                        except Exception:
-                            pass
-                    cond.notify_all()
-
-        threads = [threading.Thread(target=run, args=(i,)) for i in range(n)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-        return optima
+        """One scipy L-BFGS-B per restart, their objective calls evaluated together by
+        ``log_marginal_likelihood_batch`` (see ``gpry_b200.lockstep``)."""
+        def batch(thetas):
+            lml, grad = self.log_marginal_likelihood_batch(thetas, eval_gradient=True)
+            return -lml, -grad
+        return lockstep_minimize(batch, theta_initials, bounds)
 
     # ------------------------------------------------------------------ model update
     def _update_model(self):
@@ -600,16 +575,21 @@ class GaussianProcessRegressor:
         matrix is built on the device from ``kernel_``, so the argument is ignored."""
         kind, _, _ = self._kernel_spec()
         N = len(self.y_train_)
-        L, V, alpha_, _, info = workspace(self.device).factorize(
+        if self._dev is None:
+            self._dev = DeviceGP(self.device)
+        self._factor_resident = False      # whatever was resident is overwritten from here on
+        _, _, alpha_, _, info = self._dev.factorize(
             kind, self.X_train_, np.broadcast_to(self.alpha, (N,)), self.y_train_,
-            self.kernel_.theta)
+            self.kernel_.theta, want_L=False, want_V=False, keep_on_device=True)
         if info != 0:
             raise np.linalg.LinAlgError(
                 "The kernel, %s, is not returning a positive definite matrix. Try gradually "
                 "increasing the 'noise_level' parameter of your GaussianProcessRegressor "
                 "estimator." % self.kernel_,
                 f"{info}-th leading minor of the array is not positive definite")
-        self.L_, self.V_, self.alpha_ = L, V, alpha_
+        self._L = self._V = None           # fetched from the device on first access
+        self.alpha_ = alpha_
+        self._factor_resident = True
         self._dev_dirty = True
 
     # ------------------------------------------------------------------ device state
@@ -637,10 +617,40 @@ class GaussianProcessRegressor:
             if self.clip_factor is not None:   # gpr.py:1187-1195
                 clip_hi = (self.clip_factor * max(self.y_train)
                            - (self.clip_factor - 1) * min(self.y_train))
-            self._dev.upload(kind, self.X_train_, self.alpha_, self.V_, c, ell, x_min, x_width,
-                             y_mean, y_std, clip_hi)
+            if self._factor_resident:      # straight from the factorisation, no N^2 transfer
+                self._dev.adopt_factorization(c, ell, x_min, x_width, y_mean, y_std, clip_hi)
+            else:
+                if self.V_ is None:
+                    raise ValueError("the model has no valid factorisation (not fit to data "
+                                     "yet, or the last factorisation failed)")
+                self._dev.upload(kind, self.X_train_, self.alpha_, self.V_, c, ell, x_min,
+                                 x_width, y_mean, y_std, clip_hi)
             self._dev_dirty = False
+            self._clf_bound = None          # an upload clears the device-side classifier
+        clf = self.infinities_classifier
+        if self._classifier_on_device():
+            tag = (id(clf), clf.version)
+            if self._clf_bound != tag:
+                spec = clf.device_spec()
+                self._clf_const = spec[1] if spec[0] == "all" else None
+                self._dev.set_classifier(None if spec[0] == "all" else spec[1:])
+                self._clf_bound = tag
+        elif self._clf_bound is not None:
+            self._dev.set_classifier(None)
+            self._clf_bound = self._clf_const = None
         return self._dev
+
+    def _classifier_on_device(self):
+        """True if the infinities classifier can be evaluated by the library (``gpry_b200.svm``
+        or anything else exposing ``device_spec``) and has been trained."""
+        clf = self.infinities_classifier
+        return clf is not None and hasattr(clf, "device_spec") and clf.y_train is not None
+
+    def _set_masks(self, dev, trust=True):
+        """Per-call device masks: ``minus_inf_value`` is read at call time (gp_acquisition.py:
+        788-792 changes it temporarily), the trust region can be switched off per call."""
+        dev.set_mask_value(self.minus_inf_value)
+        dev.set_trust_region(self.trust_bounds if trust else None, self.minus_inf_value)
 
     # ------------------------------------------------------------------ predict
     @staticmethod
@@ -666,44 +676,53 @@ class GaussianProcessRegressor:
             raise ValueError("Mean grad and std grad not implemented for n_samples > 1")
         X = self._as_2d(X, validate)
         impose_trust_region = self.trust_bounds is not None and not ignore_trust_region
-        # without a classifier the trust-region mask is applied on the device (no O(M d) host
-        # pass over large pools); with one, rows are re-packed on the host anyway
-        trust_on_device = impose_trust_region and self.infinities_classifier is None
+        clf = self.infinities_classifier
+        clf_on_device = self._classifier_on_device()
+        host_clf = clf is not None and not clf_on_device
+        # the masks are applied on the device (no O(M d) host pass over large pools) unless
+        # the classifier is a foreign host object: then rows are re-packed on the host anyway
         i_outside_trust = None
-        if impose_trust_region and not trust_on_device:
+        if impose_trust_region and host_clf:
             i_outside_trust = np.logical_not(is_in_bounds(X, self.trust_bounds))
         finite = None
-        if self.infinities_classifier is not None:   # gpr.py:1136-1174
+        dev = None
+        n_samples, n_dims = X.shape
+        all_infinite = False
+        if host_clf:   # gpr.py:1136-1174
             X = np.copy(X)
-            n_samples, n_dims = X.shape
             y_mean_full = np.ones(n_samples)
             y_std_full = np.zeros(n_samples)
             grad_mean_full = np.ones((n_samples, n_dims))
             grad_std_full = np.zeros((n_samples, n_dims))
             X_ = self.preprocessing_X.transform(X)
-            finite = self.infinities_classifier.predict(np.ascontiguousarray(X_),
-                                                        validate=validate)
-            if np.all(~finite):
-                y_mean = y_mean_full * self.minus_inf_value
-                out = [y_mean]
-                if return_std:
-                    out.append(np.zeros(n_samples))
-                if return_mean_grad:
-                    out.append(np.ones((n_samples, n_dims)) * self.inf_value)
-                if return_std_grad:
-                    out.append(np.zeros((n_samples, n_dims)))
-                return out[0] if len(out) == 1 else tuple(out)
+            finite = clf.predict(np.ascontiguousarray(X_), validate=validate)
+            all_infinite = bool(np.all(~finite))
+        elif clf_on_device:
+            dev = self._device_state()
+            all_infinite = self._clf_const is False
+            if not all_infinite and self._clf_const is None and return_mean_grad:
+                all_infinite = not dev.classify(X)[0] > 0      # one point (checked above)
+        if all_infinite:
+            y_mean = np.ones(n_samples) * self.minus_inf_value
+            out = [y_mean]
+            if return_std:
+                out.append(np.zeros(n_samples))
+            if return_mean_grad:
+                out.append(np.ones((n_samples, n_dims)) * self.inf_value)
+            if return_std_grad:
+                out.append(np.zeros((n_samples, n_dims)))
+            return out[0] if len(out) == 1 else tuple(out)
+        if host_clf:
             y_mean_full[~finite] = self.minus_inf_value
             grad_mean_full[~finite] = self.inf_value
             X = X[finite]
-        dev = self._device_state()
-        dev.set_trust_region(self.trust_bounds if trust_on_device else None,
-                             self.minus_inf_value)
+        dev = self._device_state() if dev is None else dev
+        self._set_masks(dev, trust=impose_trust_region and not host_clf)
         y_mean, y_std = dev.predict(X, return_mean=True, return_std=return_std)
         if finite is not None:
             y_mean_full[finite] = y_mean
             y_mean = y_mean_full
-        if impose_trust_region and not trust_on_device:
+        if i_outside_trust is not None:
             y_mean[i_outside_trust] = self.minus_inf_value
         if return_std:
             if finite is not None:
@@ -729,47 +748,127 @@ class GaussianProcessRegressor:
             return y_mean, grad_mean
         return y_mean
 
+    def predict_grad_batch(self, X, return_std_grad=True, validate=True,
+                           ignore_trust_region=False):
+        """Row-wise equivalent of ``predict(x, return_std=True, return_mean_grad=True,
+        return_std_grad=True)`` (gpr.py:1022-1273, which accepts one point per call) for M
+        points in one device pass: ``(mean (M,), std (M,), grad_mean (M, d), grad_std (M, d))``.
+        Same conventions per row: gradients w.r.t. the transformed coordinate, rows the
+        classifier calls infinite get ``(minus_inf_value, 0, inf_value, 0)``, the trust region
+        touches the mean only, ``grad_std = 0`` where ``std`` is numerically zero."""
+        self.n_eval += len(X)
+        X = self._as_2d(X, validate)
+        n_samples, n_dims = X.shape
+        finite = None
+        if self.infinities_classifier is not None:
+            X_ = self.preprocessing_X.transform(X)
+            finite = np.asarray(self.infinities_classifier.predict(
+                np.ascontiguousarray(X_), validate=validate), dtype=bool)
+        y_mean = np.full(n_samples, self.minus_inf_value, dtype=float)
+        y_std = np.zeros(n_samples)
+        grad_mean = np.full((n_samples, n_dims), self.inf_value, dtype=float)
+        grad_std = np.zeros((n_samples, n_dims))
+        rows = np.arange(n_samples) if finite is None else np.flatnonzero(finite)
+        dev = self._device_state()
+        for lo in range(0, len(rows), 8192):
+            sel = rows[lo:lo + 8192]
+            m, sd, gm, gs = dev.predict_grad(X[sel], return_std_grad=return_std_grad)
+            y_mean[sel], y_std[sel], grad_mean[sel] = m, sd, gm
+            if return_std_grad:
+                gs[np.abs(sd) <= 1e-8] = 0.0       # ``np.allclose(y_std, 0)``, gpr.py:1248
+                grad_std[sel] = gs
+        if self.trust_bounds is not None and not ignore_trust_region:
+            y_mean[np.logical_not(is_in_bounds(X, self.trust_bounds))] = self.minus_inf_value
+        if return_std_grad:
+            return y_mean, y_std, grad_mean, grad_std
+        return y_mean, y_std, grad_mean
+
     def predict_std(self, X, validate=True):
         """gpr.py:1275-1352 (no trust region)."""
         self.n_eval += len(X)
         X = self._as_2d(X, validate)
+        clf = self.infinities_classifier
         finite = None
-        if self.infinities_classifier is not None:
+        if clf is not None and not self._classifier_on_device():
             X = np.copy(X)
             n_samples = X.shape[0]
             y_std_full = np.zeros(n_samples)
             X_ = self.preprocessing_X.transform(X)
-            finite = self.infinities_classifier.predict(np.ascontiguousarray(X_),
-                                                        validate=validate)
+            finite = clf.predict(np.ascontiguousarray(X_), validate=validate)
             if np.all(~finite):
                 return np.zeros(n_samples)
             X = X[finite]
-        _, y_std = self._device_state().predict(X, return_mean=False, return_std=True)
+        dev = self._device_state()
+        if self._clf_const is False:
+            return np.zeros(X.shape[0])
+        self._set_masks(dev, trust=False)
+        _, y_std = dev.predict(X, return_mean=False, return_std=True)
         if finite is not None:
             y_std_full[finite] = y_std
             y_std = y_std_full
         return y_std
 
     # ------------------------------------------------------------------ fused fast paths
-    def predict_logexp(self, X, zeta, noise_level=None, stream=None):
-        """mean, std and LogExp acquisition in one device pass (NORA's scoring,
-        mpi.py:182-218 + gp_acquisition.py:1049-1051, 1123-1124).  No classifier / trust
-        region masks are applied (as in ``LogExp.f``); counts ``len(X)`` evaluations."""
-        self.n_eval += len(X)
+    def _scalar_noise(self, noise_level):
         noise_level = self.noise_level if noise_level is None else noise_level
-        if np.iterable(noise_level):
-            noise_level = float(np.mean(noise_level))
-        return self._device_state().predict_logexp(X, zeta, noise_level, self.y_max,
-                                                   stream=stream)
+        return float(np.mean(noise_level)) if np.iterable(noise_level) else noise_level
+
+    def _host_classifier_rows(self, X):
+        """Rows a foreign (host-side) classifier calls finite, or None if there is nothing to
+        do on the host (no classifier, or one the library evaluates itself)."""
+        clf = self.infinities_classifier
+        if clf is None or self._classifier_on_device():
+            return None
+        if hasattr(X, "is_cuda"):
+            raise NotImplementedError("a host-side classifier cannot mask device-resident "
+                                      "candidates; use account_for_inf='SVM' (gpry_b200.svm)")
+        X_ = self.preprocessing_X.transform(np.asarray(X, dtype=float))
+        return np.flatnonzero(clf.predict(np.ascontiguousarray(X_), validate=False))
+
+    def predict_logexp(self, X, zeta, noise_level=None, stream=None):
+        """mean, std and LogExp acquisition in one device pass (NORA's scoring: mpi.py:182-218
+        calls ``predict`` -- with its classifier and trust-region masks -- and
+        gp_acquisition.py:1049-1051, 1123-1124 apply ``LogExp.f``): masked rows come out as
+        ``(minus_inf_value, 0 | std, -inf)``.  Counts ``len(X)`` evaluations."""
+        self.n_eval += len(X)
+        noise_level = self._scalar_noise(noise_level)
+        dev = self._device_state()
+        self._set_masks(dev, trust=self.trust_bounds is not None)
+        rows = self._host_classifier_rows(X)
+        if rows is None:
+            mean, std, acq = dev.predict_logexp(X, zeta, noise_level, self.y_max, stream=stream)
+            if self._clf_const is False:
+                mean[:], std[:], acq[:] = self.minus_inf_value, 0.0, -np.inf
+            return mean, std, acq
+        M = len(X)
+        mean, std = np.full(M, self.minus_inf_value, dtype=float), np.zeros(M)
+        acq = np.full(M, -np.inf)
+        if len(rows):
+            mean[rows], std[rows], acq[rows] = dev.predict_logexp(
+                np.ascontiguousarray(np.asarray(X, dtype=float)[rows]), zeta, noise_level,
+                self.y_max, stream=stream)
+        return mean, std, acq
 
     def predict_logexp_topk(self, X, zeta, Kp, noise_level=None, idx_offset=0, stream=None,
                             device_out=False, want_X=True):
         """Fused scoring + descending-acquisition pre-ranking: only the Kp best candidates
-        leave the GPU.  Returns (acq, idx, mean, std, X)."""
+        leave the GPU.  Returns (acq, idx, mean, std, X); masks as in ``predict_logexp``."""
         self.n_eval += len(X)
-        noise_level = self.noise_level if noise_level is None else noise_level
-        if np.iterable(noise_level):
-            noise_level = float(np.mean(noise_level))
-        return self._device_state().predict_logexp_topk(
-            X, zeta, noise_level, self.y_max, Kp, idx_offset=idx_offset, stream=stream,
-            device_out=device_out, want_X=want_X)
+        noise_level = self._scalar_noise(noise_level)
+        dev = self._device_state()
+        self._set_masks(dev, trust=self.trust_bounds is not None)
+        rows = self._host_classifier_rows(X)
+        if rows is None:
+            out = dev.predict_logexp_topk(X, zeta, noise_level, self.y_max, Kp,
+                                          idx_offset=idx_offset, stream=stream,
+                                          device_out=device_out, want_X=want_X)
+            if self._clf_const is False:
+                out[0][:], out[2][:], out[3][:] = -np.inf, self.minus_inf_value, 0.0
+            return out
+        Xf = np.ascontiguousarray(np.asarray(X, dtype=float)[rows])
+        if not len(rows):
+            return (np.empty(0), np.empty(0, dtype=np.int64), np.empty(0), np.empty(0),
+                    np.empty((0, self.d)) if want_X else None)
+        a, i, m, sd, Xs = dev.predict_logexp_topk(Xf, zeta, noise_level, self.y_max, Kp,
+                                                  idx_offset=0, stream=stream, want_X=want_X)
+        return a, rows[i] + idx_offset, m, sd, Xs

@@ -85,7 +85,8 @@ int gpry_state_destroy(gpry_state* st);
 /*
  * Upload a fitted model.  X_train_t is the TRANSFORMED training set (N x d, row major),
  * alpha_ (N), V (N x N row major, lower triangular = L^-1; the strict upper triangle is
- * ignored).  c = constant_value, ell[d] = length scales.  Candidates are transformed on the
+ * ignored; V = NULL uploads a mean-only model: any std / acquisition request then fails with
+ * GPRY_ERR_STATE).  c = constant_value, ell[d] = length scales.  Candidates are transformed on the
  * device as ((x - x_min) / x_width) / ell  (identity: x_min = 0, x_width = 1).  Outputs are
  * de-normalised as mean * y_std + y_mean, std * y_std (identity: 0, 1) and the mean is
  * clipped above at clip_hi (+inf = no clipping).  All pointers are host pointers.
@@ -101,12 +102,34 @@ int gpry_state_adopt_factorization(gpry_state* st, double c, const double* ell,
                                    const double* x_min, const double* x_width,
                                    double y_mean, double y_std, double clip_hi);
 
-/* Trust region applied ON THE DEVICE to the mean returned by gpry_predict (not to the std, not
- * to the acquisition entry points): candidates outside [lower, upper] (un-transformed, d
- * entries each, host pointers) get mean = value (gpr.py:1104-1109, 1200-1201 with
- * tools.py:263-287).  lower = upper = NULL switches it off.  Stays set across uploads. */
+/* Trust region applied ON THE DEVICE: candidates outside [lower, upper] (un-transformed, d
+ * entries each, host pointers, bounds inclusive) get mean = value (gpr.py:1104-1109, 1200-1201
+ * with tools.py:263-287) and, in the acquisition entry points, acq = -inf (LogExp of a
+ * non-finite mean, acquisition_functions.py:983-992); the std is not touched.
+ * lower = upper = NULL switches it off.  Stays set across uploads. */
 int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const double* upper,
                           double value);
+
+/* The value written by the two masks (GaussianProcessRegressor.minus_inf_value, read at call
+ * time by the reference: gpr.py:1145, 1201; gp_acquisition.py:788-792 changes it temporarily). */
+int gpry_set_mask_value(gpry_state* st, double value);
+
+/*
+ * Infinities classifier evaluated ON THE DEVICE (svm.py:308-346 SVM.predict = sign of the
+ * decision function of a two-class RBF SVC; called by predict / predict_std on every pool,
+ * gpr.py:1136-1174, 1300-1318):  decision(x) = sum_i dual_coef[i] exp(-gamma |x_ - sv_i|^2)
+ * + intercept, with x_ the transformed candidate (the (x_min, x_width) of the uploaded model)
+ * and sv (n_sv x d, row major) given in that transformed space.  While set, rows with
+ * decision <= 0 come out of gpry_predict / gpry_predict_logexp / gpry_predict_logexp_topk
+ * with mean = mask value, std = 0, acq = -inf, so the mask never crosses PCIe.  Host pointers;
+ * sv = NULL switches it off; every gpry_state_upload / adopt_factorization clears it.
+ */
+int gpry_set_classifier(gpry_state* st, int n_sv, int d, const double* sv,
+                        const double* dual_coef, double intercept, double gamma);
+
+/* Decision values for M un-transformed candidates (host or device per `where`). */
+int gpry_classify(gpry_state* st, const double* X, int64_t M, int where, double* out_decision,
+                  void* stream);
 
 /* Query what is loaded: N, d, kind (any may be NULL). Returns GPRY_ERR_STATE if empty. */
 int gpry_state_info(const gpry_state* st, int* N, int* d, int* kind);
@@ -147,6 +170,15 @@ int gpry_mean_grad(gpry_state* st, const double* x, double* out_grad);
  * y_std twice as the reference does; zero if the variance vanishes.  Host pointers. */
 int gpry_std_grad(gpry_state* st, const double* x, double* out_grad, double* out_std);
 
+/* Batched version of the two calls above for the acquisition optimiser's many starts
+ * (gp_acquisition.py:280-390 runs them one L-BFGS-B at a time; acquisition_functions.py:
+ * 967-1007 consumes mean, std and both gradients): X (M x d, un-transformed, 1 <= M <= 8192),
+ * out_mean / out_std (M), out_grad_mean / out_grad_std (M x d); any output may be NULL.  Same
+ * conventions per row as gpry_predict (no trust region), gpry_mean_grad and gpry_std_grad.
+ * Host pointers. */
+int gpry_predict_grad(gpry_state* st, const double* X, int M, double* out_mean, double* out_std,
+                      double* out_grad_mean, double* out_grad_std);
+
 /*
  * Posterior covariance (normalised units, prior variance c on the diagonal minus the explained
  * part, NO noise term) among Ka <= 8192 candidates X (Ka x d, un-transformed):
@@ -178,6 +210,12 @@ int gpry_factorize(gpry_state* st, int kind, int N, int d, const double* X_train
                    const double* noise2, const double* y_t, const double* theta,
                    double* out_L, double* out_V, double* out_alpha,
                    double* out_logdet_half, int* info, int keep_on_device);
+
+/* L and / or V (N x N row major, lower, upper triangle zeroed; either may be NULL) of the
+ * factorisation kept resident by the last gpry_factorize(..., keep_on_device = 1) on this
+ * state: lets the host attributes L_ / V_ (gpr.py:1456-1457) be fetched only when something
+ * reads them.  GPRY_ERR_STATE if no factorisation is resident.  Host pointers. */
+int gpry_factor_download(gpry_state* st, double* out_L, double* out_V);
 
 /*
  * Log marginal likelihood (and its gradient w.r.t. theta if out_grad != NULL) for B

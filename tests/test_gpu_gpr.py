@@ -339,7 +339,8 @@ def test_classifier_and_trust_region_masks():
 def test_trust_region_mask_on_device():
     """Without a classifier the trust-region mask (gpr.py:1104-1109, 1200-1201; inclusive bounds
     as tools.py:287) is applied by the library: same rows, same values as the host mask, std
-    untouched, ignore_trust_region / predict_std / the acquisition calls unaffected."""
+    untouched, ignore_trust_region / predict_std unaffected, acquisition = -inf outside."""
+    from gpry_b200.acquisition_functions import LogExp
     from gpry_b200.gpr import GaussianProcessRegressor
     from gpry_b200.preprocessing import Normalize_bounds, Normalize_y
     g = load_golden("rbf_d8_n300")
@@ -377,4 +378,9 @@ def test_trust_region_mask_on_device():
     zeta, sn = 1.3, gpr.noise_level
     a0 = plain.predict_logexp(Xc, zeta, sn)[2]
     a1 = gpr.predict_logexp(Xc, zeta, sn)[2]
-    assert np.array_equal(a0, a1)
+    # the acquisition calls see the masked mean (reference: compute_y_parallel -> predict)
+    assert np.all(a1[out] == -np.inf) and np.array_equal(a0[~out], a1[~out])
+    acq_call = LogExp(zeta=zeta)(Xc, gpr)
+    assert np.all(acq_call[out] == -np.inf)
+    fin = ~out & np.isfinite(a0)
+    assert np.array_equal(acq_call[fin], a0[fin])
