@@ -55,6 +55,15 @@ def _worker(rank, world, port, out_dir):
     nora = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=128)
     X_pool, y_pool, acq_pool = nora.multi_add(gpr2, n_points=int(g["pool_n_points"]), X_mc=Xp)
     assert np.array_equal(X_pool, Xp[g["pool_idx_single_sort_acq"]])
+    # --- BatchOptimizer: restarts split over the ranks, every rank returns the same batch
+    from gpry_b200.gp_acquisition import BatchOptimizer
+    opt = BatchOptimizer(g["bounds"], preprocessing_X=Normalize_bounds(g["bounds"]),
+                         n_restarts_optimizer=6, verbose=0)
+    Xb, yb, ab = opt.multi_add(gpr2, n_points=2, rng=np.random.default_rng(50 + rank))
+    both = parallel.allgather((Xb, yb, ab))
+    assert all(np.array_equal(b[0], both[0][0]) and np.array_equal(b[2], both[0][2])
+               for b in both)
+    assert Xb.shape == (2, g["d"]) and np.all(np.isfinite(ab))
     np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.array([best_rank]))
     dist.barrier()
     dist.destroy_process_group()
