@@ -48,6 +48,8 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-secondary", action="store_true")
+    p.add_argument("--contract", choices=("fp64", "int8"), default="fp64",
+                   help="variance contraction: FP64 DMMA or the exact INT8 split (tcgen05)")
     return p.parse_args()
 
 
@@ -328,6 +330,7 @@ def run_ours(args):
     dev_t = torch.device("cuda", local)
     N, d, M, Kp = args.ntrain, args.dim, args.pool, args.kp
     dev = DeviceGP(local)
+    dev.set_contract_mode(args.contract)
 
     # ---- model: fitted on rank 0, broadcast once (per refit), uploaded on every GPU ----
     if rank == 0:

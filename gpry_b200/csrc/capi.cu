@@ -174,6 +174,7 @@ int gpry_state_destroy(gpry_state* st) {
     st->tmp.release(); st->small.release(); st->Vrm.release(); st->trust.release();
     st->pc_U.release(); st->pc_Ks.release(); st->pc_UT.release(); st->pc_G.release();
     st->VTrm.release(); st->gr_out.release(); st->clf_dec.release();
+    st->oz_Ksl.release(); st->oz_Vs.release(); st->oz_scale.release(); st->oz_rb.release();
     if (st->clf) gpry_state_destroy(st->clf);
     st->f_K.release(); st->f_VT.release(); st->f_W.release(); st->f_TT.release();
     st->f_Winv.release(); st->f_misc.release(); st->f_prob.release();
@@ -231,6 +232,14 @@ int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const doub
     GPRY_CUDA(cudaMemcpy(st->trust.p, h.data(), 2 * MAX_DIM * 8, cudaMemcpyHostToDevice));
     st->trust_value = value;
     st->trust_on = true;
+  });
+}
+
+int gpry_set_contract_mode(gpry_state* st, int mode) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    GPRY_CHECK_ARG(mode == GPRY_CONTRACT_FP64 || mode == GPRY_CONTRACT_INT8, "unknown mode");
+    st->contract_mode = mode;
   });
 }
 

@@ -51,6 +51,18 @@ constexpr int TILE_DOUBLES = TILE_ROWS * TILE_K;        // 2048
 constexpr int TILE_BYTES = TILE_DOUBLES * 8;            // 16384
 constexpr int KT_PER_BLOCK = TILE_ROWS / TILE_K;        // k-tiles per 128-row block = 8
 
+// ---------------------------------------------------------------------------------------
+// INT8 split of the FP64 variance contraction (ozaki.cu): operands as OZ_NS balanced base-256
+// digits; tcgen05.mma kind::i8 tiles of 128 candidates x OZ_ROWS rows of V x OZ_KC k.
+// ---------------------------------------------------------------------------------------
+constexpr int OZ_NS = 7;                                // int8 slices per operand
+constexpr int OZ_ROWS = 64;                             // rows of V per MMA (N dimension)
+constexpr int OZ_KC = 32;                               // k per MMA (32 int8)
+constexpr int OZ_A_BYTES = TILE_ROWS * OZ_KC;           // one K* slice of one chunk: 4096
+constexpr int OZ_B_BYTES = OZ_ROWS * OZ_KC;             // one V slice of one chunk: 2048
+constexpr int OZ_STAGE_BYTES = OZ_NS * (OZ_A_BYTES + OZ_B_BYTES);   // 43008
+constexpr int OZ_STAGES = 5;
+
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // offset (in tiles) of V tile (jb, kt), kt < (jb+1)*8, lower block triangle packed by rows

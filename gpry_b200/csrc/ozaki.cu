@@ -1,0 +1,309 @@
+// Variance contraction on the INT8 tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
+//
+// ssq_i = sum_j (sum_k V_jk k*_ik)^2 is ~97 % of the flops of predict(return_std) and runs at
+// the FP64 tensor peak in predict.cu (DMMA, 0.99 of cuBLAS DGEMM).  B200's INT8 tensor pipe is
+// two orders of magnitude faster than its FP64 pipe, so the product is re-expressed exactly in
+// integers (the "Ozaki scheme"):
+//   k*_ik / c      in [0, 1]  -> round(. 2^54) = sum_p a_p 256^(6-p),  a_p int8 (balanced digits)
+//   V_jk / 2^e_j   in (-1, 1) -> round(. 2^54) = sum_q b_q 256^(6-q),  e_j: exponent of max_k |V_jk|
+//   sum_k V_jk k*_ik = c 2^e_j 2^-12 sum_g 256^-g S_g,   S_g = sum_{p+q=g} sum_k a_p b_q
+// Every S_g is an exact int32 sum (|S_g| <= 7 N 2^14 < 2^31 for N <= 16384); groups g <= 6 are
+// kept (28 digit products), which leaves a relative error of ~2^-50 per row, the size of the
+// rounding error of an FP64 dot product of this length.  The digits of K* are produced by
+// kstar_build (predict.cu, WMODE 2), the digits of V once per upload (slice_v_kernel).
+//
+// oz_contract_kernel: one CTA per (row split, candidate tile); warp 4 streams the operand
+// chunks with TMA bulk copies into a 5-stage ring, one thread of warp 5 issues the 28 MMAs of a
+// chunk (128 candidates x 64 rows x 32 k each, 7 accumulators of 64 columns in TMEM), warps 0-3
+// read the accumulators back after the last chunk of a row block (thread = candidate), rebuild
+// the FP64 row products and accumulate their squares.
+#include "state.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace gpry {
+
+namespace {
+
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // K-major, no swizzle: 8 rows x 16 B core matrices (128 contiguous bytes); SBO between 8-row
+  // groups, LBO between the two 16-byte k halves; descriptor version 1 (sm_100)
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
+constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) |
+                              ((uint32_t)(OZ_ROWS >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
+
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(OZ_IDESC), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void oz_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// a wait that cannot hang the GPU: traps after ~seconds
+__device__ __forceinline__ void oz_wait(uint64_t* bar, uint32_t parity) {
+  for (long long it = 0; it < 400000000LL; it++)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+#define OZ_TMEM_LD16(taddr, r)                                                                   \
+  asm volatile(                                                                                  \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                  \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                          \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),      \
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), \
+        "=r"(r[14]), "=r"(r[15])                                                                 \
+      : "r"(taddr))
+
+constexpr int OZ_THREADS = 192;   // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer
+constexpr size_t OZ_SMEM = (size_t)OZ_STAGES * OZ_STAGE_BYTES + 256;
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__ Vs, int nKC,
+                   const double* __restrict__ row_scale, const int* __restrict__ rb_list,
+                   const int* __restrict__ rb_count, int max_rb, double* __restrict__ ssqp,
+                   int chunk_cands) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)OZ_STAGES * OZ_STAGE_BYTES);
+  uint64_t* empty = full + OZ_STAGES;
+  uint64_t* tmem_full = empty + OZ_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x, tile = blockIdx.y;
+  const int n_rb = rb_count[split];
+  const int* my_rb = rb_list + (size_t)split * max_rb;
+
+  if (tid == 0) {
+    for (int s = 0; s < OZ_STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 128);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {   // ---- producer: one 28 KB + one 14 KB bulk copy per chunk
+      const uint8_t* Abase = Ksl + (size_t)tile * nKC * (size_t)(OZ_NS * OZ_A_BYTES);
+      int it = 0;
+      for (int r = 0; r < n_rb; r++) {
+        const int rb = my_rb[r];
+        const uint8_t* Bbase = Vs + (size_t)rb * nKC * (size_t)(OZ_NS * OZ_B_BYTES);
+        const int nch = 2 * (rb + 1);      // rows 64 rb .. 64 rb + 63 are zero beyond k = 64 (rb + 1)
+        for (int kc = 0; kc < nch; kc++, it++) {
+          const int s = it % OZ_STAGES;
+          oz_wait(&empty[s], ((it / OZ_STAGES) & 1) ^ 1);
+          uint8_t* dst = smem + (size_t)s * OZ_STAGE_BYTES;
+          mbar_expect_tx(&full[s], OZ_STAGE_BYTES);
+          tma_bulk_g2s(dst, Abase + (size_t)kc * (OZ_NS * OZ_A_BYTES), OZ_NS * OZ_A_BYTES, &full[s]);
+          tma_bulk_g2s(dst + OZ_NS * OZ_A_BYTES, Bbase + (size_t)kc * (OZ_NS * OZ_B_BYTES),
+                       OZ_NS * OZ_B_BYTES, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {   // ---- MMA issuer
+      int it = 0;
+      for (int r = 0; r < n_rb; r++) {
+        const int nch = 2 * (my_rb[r] + 1);
+        oz_wait(tmem_empty, (r & 1) ^ 1);          // epilogue has drained the accumulators
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kc = 0; kc < nch; kc++, it++) {
+          const int s = it % OZ_STAGES;
+          oz_wait(&full[s], (it / OZ_STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + (size_t)s * OZ_STAGE_BYTES);
+          const uint64_t da0 = oz_desc(sa, OZ_A_BYTES / 2, 128);
+          const uint64_t db0 = oz_desc(sa + OZ_NS * OZ_A_BYTES, OZ_B_BYTES / 2, 128);
+          const uint32_t first = kc > 0 ? 1u : 0u;
+#pragma unroll
+          for (int g = 0; g < OZ_NS; g++) {
+#pragma unroll
+            for (int p = 0; p <= g; p++)
+              oz_mma(tmem + (uint32_t)(g * OZ_ROWS), da0 + (uint64_t)((p * OZ_A_BYTES) >> 4),
+                     db0 + (uint64_t)(((g - p) * OZ_B_BYTES) >> 4), p > 0 ? 1u : first);
+          }
+          oz_commit(&empty[s]);        // frees the ring slot once these MMAs have read it
+        }
+        oz_commit(tmem_full);          // all products of this row block are in TMEM
+      }
+    }
+  } else {
+    // ---- epilogue: thread = candidate (TMEM lane), 64 columns = rows of V, 7 digit groups
+    double ssq = 0.0;
+    for (int r = 0; r < n_rb; r++) {
+      const int rb = my_rb[r];
+      oz_wait(tmem_full, r & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < OZ_ROWS; cc += 16) {
+        uint32_t v[OZ_NS][16];
+#pragma unroll
+        for (int g = 0; g < OZ_NS; g++) OZ_TMEM_LD16(lane_base + (uint32_t)(g * OZ_ROWS + cc), v[g]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          double acc = (double)(int)v[OZ_NS - 1][c];
+#pragma unroll
+          for (int g = OZ_NS - 2; g >= 0; g--) acc = fma(acc, 0.00390625, (double)(int)v[g][c]);
+          const double w = acc * __ldg(row_scale + rb * OZ_ROWS + cc + c);
+          ssq = fma(w, w, ssq);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      oz_arrive(tmem_empty);
+    }
+    ssqp[(size_t)split * chunk_cands + tile * TILE_ROWS + tid] = ssq;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u)
+                 : "memory");
+}
+
+// per row of V (row-major, padded to Np): 2^e with |V_jk| / 2^e < 1
+__global__ void __launch_bounds__(256)
+oz_row_exponent_kernel(const double* __restrict__ Vrm, int Np, double* __restrict__ row_pow2) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= Np) return;
+  double mx = 0.0;
+  for (int k = lane; k <= j; k += 32) mx = fmax(mx, fabs(Vrm[(size_t)j * Np + k]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) {
+    int e = 0;
+    if (mx > 0.0) frexp(mx, &e);       // mx = m 2^e, m in [0.5, 1)
+    row_pow2[j] = ldexp(1.0, e);
+  }
+}
+// digits of V: thread per (row j, 16 consecutive k); layout [row block of 64][k chunk of 32][slice]
+// [k16 (2)][row (64)][16 B]
+__global__ void __launch_bounds__(256)
+oz_slice_v_kernel(const double* __restrict__ Vrm, int Np, const double* __restrict__ row_pow2,
+                  uint8_t* __restrict__ Vs) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n16 = Np / 16;
+  if (e >= (int64_t)Np * n16) return;
+  const int j = (int)(e / n16), k0 = (int)(e % n16) * 16;
+  const double sc = 18014398509481984.0 / row_pow2[j];     // 2^54 / 2^e_j (exact)
+  uint32_t packs[OZ_NS][4];
+#pragma unroll
+  for (int p = 0; p < OZ_NS; p++)
+#pragma unroll
+    for (int w = 0; w < 4; w++) packs[p][w] = 0u;
+#pragma unroll
+  for (int b = 0; b < 16; b++) {
+    const int k = k0 + b;
+    const double val = k <= j ? Vrm[(size_t)j * Np + k] : 0.0;
+    long long t = __double2ll_rn(val * sc);
+#pragma unroll
+    for (int p = OZ_NS - 1; p >= 1; p--) {
+      const int dg = (int)(signed char)(t & 0xFF);
+      t = (t - dg) >> 8;
+      packs[p][b >> 2] |= (uint32_t)(dg & 0xFF) << (8 * (b & 3));
+    }
+    packs[0][b >> 2] |= (uint32_t)((int)t & 0xFF) << (8 * (b & 3));
+  }
+  const int nKC = Np / OZ_KC;
+  uint8_t* base = Vs + ((size_t)(j / OZ_ROWS) * nKC + (k0 >> 5)) * (size_t)(OZ_NS * OZ_B_BYTES) +
+                  ((k0 >> 4) & 1) * (OZ_B_BYTES / 2) + (j % OZ_ROWS) * 16;
+#pragma unroll
+  for (int p = 0; p < OZ_NS; p++)
+    *reinterpret_cast<uint4*>(base + p * OZ_B_BYTES) =
+        make_uint4(packs[p][0], packs[p][1], packs[p][2], packs[p][3]);
+}
+// row_scale[j] = c 2^e_j 2^-12
+__global__ void oz_row_scale_kernel(const double* __restrict__ row_pow2, int Np, double c,
+                                    double* __restrict__ row_scale) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < Np) row_scale[j] = c * row_pow2[j] * 0.000244140625;
+}
+
+}  // namespace
+
+bool ozaki_supported(const gpry_state* st) {
+  return st->has_V && st->d <= MAX_DIM_REG && st->Npad >= 512 && st->Npad <= 16384;
+}
+
+// digits of V and the balanced assignment of row blocks to row splits (once per upload)
+void ozaki_prepare(gpry_state* st, cudaStream_t s) {
+  if (st->oz_valid) return;
+  const int Np = st->Npad, nRB = Np / OZ_ROWS, nKC = Np / OZ_KC;
+  st->oz_Vs.reserve((size_t)nRB * nKC * OZ_NS * OZ_B_BYTES);
+  st->oz_scale.reserve(2 * (size_t)Np);
+  double* row_pow2 = st->oz_scale.p + Np;
+  oz_row_exponent_kernel<<<(Np + 7) / 8, 256, 0, s>>>(st->Vrm.p, Np, row_pow2);
+  GPRY_CUDA(cudaGetLastError());
+  const int64_t tot = (int64_t)Np * (Np / 16);
+  oz_slice_v_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(st->Vrm.p, Np, row_pow2,
+                                                                  st->oz_Vs.p);
+  GPRY_CUDA(cudaGetLastError());
+  oz_row_scale_kernel<<<(Np + 255) / 256, 256, 0, s>>>(row_pow2, Np, st->c, st->oz_scale.p);
+  GPRY_CUDA(cudaGetLastError());
+  // row blocks beyond the last training row are all zero: skip them
+  const int used_rb = (st->N + OZ_ROWS - 1) / OZ_ROWS;
+  int splits = 1;
+  while (splits < 8 && splits * 2 <= used_rb) splits *= 2;
+  if (used_rb >= 12) splits = 6;       // 24 tiles x 6 splits fill 144 of 148 SMs per wave
+  std::vector<std::vector<int>> lists(splits);
+  std::vector<long long> load(splits, 0);
+  for (int rb = used_rb - 1; rb >= 0; rb--) {       // longest first, to the least loaded split
+    int best = 0;
+    for (int q = 1; q < splits; q++)
+      if (load[q] < load[best]) best = q;
+    lists[best].push_back(rb);
+    load[best] += rb + 1;
+  }
+  int max_rb = 0;
+  for (auto& l : lists) max_rb = std::max(max_rb, (int)l.size());
+  std::vector<int> h((size_t)splits * max_rb + splits, 0);
+  for (int q = 0; q < splits; q++) {
+    for (size_t i = 0; i < lists[q].size(); i++) h[(size_t)q * max_rb + i] = lists[q][i];
+    h[(size_t)splits * max_rb + q] = (int)lists[q].size();
+  }
+  st->oz_rb.reserve(h.size());
+  GPRY_CUDA(cudaMemcpyAsync(st->oz_rb.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  GPRY_CUDA(cudaStreamSynchronize(s));
+  st->oz_splits = splits;
+  st->oz_max_rb = max_rb;
+  GPRY_CUDA(cudaFuncSetAttribute(oz_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)OZ_SMEM));
+  st->oz_valid = true;
+}
+
+size_t ozaki_kslices_bytes(const gpry_state* st, int tiles) {
+  return (size_t)tiles * (st->Npad / OZ_KC) * OZ_NS * OZ_A_BYTES;
+}
+
+// ssqp[split][chunk_cands] for `tiles` candidate tiles whose digits are in st->oz_Ksl
+void ozaki_contract(gpry_state* st, int tiles, int chunk_cands, cudaStream_t s) {
+  dim3 grid(st->oz_splits, tiles);
+  oz_contract_kernel<<<grid, OZ_THREADS, OZ_SMEM, s>>>(
+      st->oz_Ksl.p, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p,
+      st->oz_rb.p + (size_t)st->oz_splits * st->oz_max_rb, st->oz_max_rb, st->ssqp.p, chunk_cands);
+  GPRY_CUDA(cudaGetLastError());
+}
+
+}  // namespace gpry

@@ -47,12 +47,12 @@ __device__ __forceinline__ double kernel_value(double r2, double c) {
 //   grid  = (tiles in chunk, JS)      block = 128 threads = the 128 candidates of a tile
 //   each block: NJ = Npad / JS training points (a multiple of 16)
 // ---------------------------------------------------------------------------------------
-template <int DP, int KIND, bool WRITE_KS>
+template <int DP, int KIND, int WMODE>
 __global__ void __launch_bounds__(128)
 kstar_build_kernel(const double* __restrict__ X, int64_t M, int d, int64_t cand0,
                    const double* __restrict__ T, const double* __restrict__ alpha, int NJ,
-                   int nKT, double c, XformParams prm, double* __restrict__ Ks,
-                   double* __restrict__ meanp, int chunk_cands) {
+                   int nKT, double c, XformParams prm, void* __restrict__ Kout,
+                   double* __restrict__ meanp, int chunk_cands, double slice_scale) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* Ts = reinterpret_cast<double*>(smem_raw);          // [NJ][DP]
   double* As = Ts + (size_t)NJ * DP;                         // [NJ]
@@ -95,29 +95,64 @@ kstar_build_kernel(const double* __restrict__ X, int64_t M, int d, int64_t cand0
   mbar_wait(bar, 0);
 
   double mp = 0.0;
-  double* kout = Ks + ((size_t)tile * nKT + (j0 >> 4)) * TILE_DOUBLES + tid * 4;
-  for (int j4 = 0; j4 < NJ; j4 += 4) {
-    double kv[4];
+  double* kout = reinterpret_cast<double*>(Kout) + ((size_t)tile * nKT + (j0 >> 4)) * TILE_DOUBLES +
+                 tid * 4;
+  for (int j16 = 0; j16 < NJ; j16 += 16) {
+    uint32_t packs[OZ_NS][4];     // WMODE 2: 16 int8 digits per slice for k = j0 + j16 .. + 15
+    if (WMODE == 2) {
 #pragma unroll
-    for (int jj = 0; jj < 4; jj++) {
-      const double2* tp = reinterpret_cast<const double2*>(Ts + (size_t)(j4 + jj) * DP);
-      double r2 = 0.0;      // summed in index order, as cdist does (sklearn:kernels.py:1569)
+      for (int p = 0; p < OZ_NS; p++)
 #pragma unroll
-      for (int k2 = 0; k2 < DP / 2; k2++) {
-        double2 t = tp[k2];
-        double d0 = u[2 * k2] - t.x;
-        r2 = fma(d0, d0, r2);
-        double d1 = u[2 * k2 + 1] - t.y;
-        r2 = fma(d1, d1, r2);
-      }
-      kv[jj] = kernel_value<KIND>(r2, c);
-      mp = fma(kv[jj], As[j4 + jj], mp);
+        for (int w = 0; w < 4; w++) packs[p][w] = 0u;
     }
-    if (WRITE_KS) {
-      // tile (j4 / 16), panel (j4 / 4) % 4, row tid
-      double* p = kout + (size_t)(j4 >> 4) * TILE_DOUBLES + ((j4 >> 2) & 3) * (TILE_ROWS * 4);
-      reinterpret_cast<double2*>(p)[0] = make_double2(kv[0], kv[1]);
-      reinterpret_cast<double2*>(p)[1] = make_double2(kv[2], kv[3]);
+#pragma unroll
+    for (int q4 = 0; q4 < 4; q4++) {
+      const int j4 = j16 + q4 * 4;
+      double kv[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const double2* tp = reinterpret_cast<const double2*>(Ts + (size_t)(j4 + jj) * DP);
+        double r2 = 0.0;      // summed in index order, as cdist does (sklearn:kernels.py:1569)
+#pragma unroll
+        for (int k2 = 0; k2 < DP / 2; k2++) {
+          double2 t = tp[k2];
+          double d0 = u[2 * k2] - t.x;
+          r2 = fma(d0, d0, r2);
+          double d1 = u[2 * k2 + 1] - t.y;
+          r2 = fma(d1, d1, r2);
+        }
+        kv[jj] = kernel_value<KIND>(r2, c);
+        mp = fma(kv[jj], As[j4 + jj], mp);
+        if (WMODE == 2) {
+          // k*/c in [0, 1] as a 55-bit fixed-point number in OZ_NS balanced base-256 digits
+          long long t = __double2ll_rn(kv[jj] * slice_scale);
+#pragma unroll
+          for (int p = OZ_NS - 1; p >= 1; p--) {
+            const int dg = (int)(signed char)(t & 0xFF);
+            t = (t - dg) >> 8;
+            packs[p][q4] |= (uint32_t)(dg & 0xFF) << (8 * jj);
+          }
+          packs[0][q4] |= (uint32_t)((int)t & 0xFF) << (8 * jj);
+        }
+      }
+      if (WMODE == 1) {
+        // tile (j4 / 16), panel (j4 / 4) % 4, row tid
+        double* p = kout + (size_t)(j4 >> 4) * TILE_DOUBLES + ((j4 >> 2) & 3) * (TILE_ROWS * 4);
+        reinterpret_cast<double2*>(p)[0] = make_double2(kv[0], kv[1]);
+        reinterpret_cast<double2*>(p)[1] = make_double2(kv[2], kv[3]);
+      }
+    }
+    if (WMODE == 2) {
+      // [tile][k-chunk of 32][slice][k16 (2)][candidate (128)][16 B]: the shared-memory image
+      // of the K-major operand of tcgen05.mma kind::i8 (ozaki.cu)
+      const int k0 = j0 + j16;
+      uint8_t* base = reinterpret_cast<uint8_t*>(Kout) +
+                      ((size_t)tile * (nKT >> 1) + (k0 >> 5)) * (size_t)(OZ_NS * OZ_A_BYTES) +
+                      ((k0 >> 4) & 1) * (OZ_A_BYTES / 2) + tid * 16;
+#pragma unroll
+      for (int p = 0; p < OZ_NS; p++)
+        *reinterpret_cast<uint4*>(base + p * OZ_A_BYTES) =
+            make_uint4(packs[p][0], packs[p][1], packs[p][2], packs[p][3]);
     }
   }
   meanp[(size_t)blockIdx.y * chunk_cands + tile * TILE_ROWS + tid] = mp;
@@ -638,28 +673,31 @@ void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_
   }
   GPRY_CUDA(cudaStreamSynchronize(s));
   st->vtrm_valid = false;
+  st->oz_valid = false;
   st->loaded = true;
 }
 
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
-template <int KIND, bool WRITE_KS>
+template <int KIND, int WMODE>
 static void launch_build(gpry_state* st, const double* dX, int64_t M, int64_t cand0, int tiles,
                          int JS, int chunk_cands, cudaStream_t s) {
   const int NJ = st->Npad / JS;
   const int d = st->d, DP = st->DP;
   dim3 grid(tiles, JS), block(128);
+  void* kout = WMODE == 2 ? (void*)st->oz_Ksl.p : (void*)st->Ks.p;
+  const double slice_scale = 18014398509481984.0 / st->c;   // 2^54 / c
   if (d <= MAX_DIM_REG) {
     size_t smem = ((size_t)NJ * DP + NJ + 128 * d + (d & 1)) * 8 + 16;
 #define GPRY_LAUNCH_BUILD(DPV)                                                                \
   case DPV: {                                                                                 \
-    auto kern = kstar_build_kernel<DPV, KIND, WRITE_KS>;                                      \
+    auto kern = kstar_build_kernel<DPV, KIND, WMODE>;                                         \
     if (smem > 48 * 1024)                                                                     \
       GPRY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                      (int)smem));                                             \
     kern<<<grid, block, smem, s>>>(dX, M, d, cand0, st->T.p, st->alpha.p, NJ, st->nKT, st->c, \
-                                   st->prm, st->Ks.p, st->meanp.p, chunk_cands);              \
+                                   st->prm, kout, st->meanp.p, chunk_cands, slice_scale);     \
   } break;
     switch (DP) {
       GPRY_LAUNCH_BUILD(4)
@@ -676,7 +714,8 @@ static void launch_build(gpry_state* st, const double* dX, int64_t M, int64_t ca
 #undef GPRY_LAUNCH_BUILD
   } else {
     size_t smem = ((size_t)NJ * DP + NJ + (size_t)DP * 129) * 8;
-    auto kern = kstar_build_generic_kernel<KIND, WRITE_KS>;
+    if (WMODE == 2) throw GpryError{GPRY_ERR_ARG, "internal: sliced K* needs d <= 32"};
+    auto kern = kstar_build_generic_kernel<KIND, WMODE == 1>;
     GPRY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, block, smem, s>>>(dX, M, d, DP, cand0, st->T.p, st->alpha.p, NJ, st->nKT, st->c,
                                    st->prm_dev.p, st->Ks.p, st->meanp.p, chunk_cands);
@@ -684,18 +723,18 @@ static void launch_build(gpry_state* st, const double* dX, int64_t M, int64_t ca
   GPRY_CUDA(cudaGetLastError());
 }
 
-template <bool WRITE_KS>
+template <int WMODE>
 static void launch_build_kind(gpry_state* st, const double* dX, int64_t M, int64_t cand0,
                               int tiles, int JS, int chunk_cands, cudaStream_t s) {
   switch (st->kind) {
     case GPRY_KERNEL_RBF:
-      launch_build<GPRY_KERNEL_RBF, WRITE_KS>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
+      launch_build<GPRY_KERNEL_RBF, WMODE>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
       break;
     case GPRY_KERNEL_MATERN15:
-      launch_build<GPRY_KERNEL_MATERN15, WRITE_KS>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
+      launch_build<GPRY_KERNEL_MATERN15, WMODE>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
       break;
     default:
-      launch_build<GPRY_KERNEL_MATERN25, WRITE_KS>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
+      launch_build<GPRY_KERNEL_MATERN25, WMODE>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
   }
 }
 
@@ -923,14 +962,22 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
   const int max_chunk_tiles = 2 * st->n_sm;
   const int chunk_tiles = (int)std::min<int64_t>(total_tiles, max_chunk_tiles);
   const int chunk_cands = chunk_tiles * TILE_ROWS;
+  // INT8 split of the contraction (ozaki.cu) when selected and the model qualifies
+  const bool ozaki = want_var && st->contract_mode == 1 && ozaki_supported(st);
+  if (ozaki) ozaki_prepare(st, s);
   // row splits: for small pools spread the row blocks of V over more CTAs
   int row_splits = 1;
-  if (want_var) {
+  if (ozaki) {
+    row_splits = st->oz_splits;
+  } else if (want_var) {
     while (row_splits * 2 <= st->nJ && (int64_t)chunk_tiles * row_splits * 2 <= st->n_sm)
       row_splits *= 2;
   }
   const int JS = choose_jsplit(st, chunk_tiles);
-  if (want_var) st->Ks.reserve((size_t)chunk_tiles * st->nKT * TILE_DOUBLES);
+  if (ozaki)
+    st->oz_Ksl.reserve(ozaki_kslices_bytes(st, chunk_tiles));
+  else if (want_var)
+    st->Ks.reserve((size_t)chunk_tiles * st->nKT * TILE_DOUBLES);
   st->meanp.reserve((size_t)JS * chunk_cands);
   if (want_var) st->ssqp.reserve((size_t)row_splits * chunk_cands);
   if (want_var)
@@ -942,10 +989,12 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
     const int n = (int)std::min<int64_t>((int64_t)tiles * TILE_ROWS, M - cand0);
     {
       TimedScope ts(st, s, T_BUILD);
-      if (want_var)
-        launch_build_kind<true>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
+      if (!want_var)
+        launch_build_kind<0>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
+      else if (ozaki)
+        launch_build_kind<2>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
       else
-        launch_build_kind<false>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
+        launch_build_kind<1>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
     }
     FinishParams fin;
     fin.meanp = st->meanp.p;
@@ -958,8 +1007,12 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
     fin.o_mean = d_mean ? d_mean + cand0 : nullptr;
     fin.o_std = d_std ? d_std + cand0 : nullptr;
     fin.o_acq = d_acq ? d_acq + cand0 : nullptr;
-    const bool fused = want_var && row_splits == 1;
-    if (want_var) {
+    const bool fused = want_var && row_splits == 1 && !ozaki;
+    if (ozaki) {
+      TimedScope ts(st, s, T_CONTRACT);
+      st->n_contract_launches += 1;
+      ozaki_contract(st, tiles, chunk_cands, s);
+    } else if (want_var) {
       TimedScope ts(st, s, T_CONTRACT);
       st->n_contract_launches += 1;
       dim3 grid(std::min(tiles, st->n_sm), row_splits);

@@ -110,6 +110,20 @@ int gpry_state_adopt_factorization(gpry_state* st, double c, const double* ell,
 int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const double* upper,
                           double value);
 
+/*
+ * How the variance contraction sum_j (sum_k V_jk k*_ik)^2 of gpr.py:1204-1208 is evaluated:
+ *   GPRY_CONTRACT_FP64 (default)  FP64 tensor cores (DMMA.8x8x4)
+ *   GPRY_CONTRACT_INT8            exact integer split of both operands into 7 int8 digits, 28
+ *                                 digit products on the INT8 tensor cores (tcgen05.mma kind::i8,
+ *                                 int32 accumulators in TMEM), recombined in FP64; same result
+ *                                 to within the rounding error of an FP64 dot product.  Used for
+ *                                 512 <= N_pad <= 16384, d <= 32 and more than 64 candidates per
+ *                                 call; other calls silently use FP64.
+ */
+#define GPRY_CONTRACT_FP64 0
+#define GPRY_CONTRACT_INT8 1
+int gpry_set_contract_mode(gpry_state* st, int mode);
+
 /* The value written by the two masks (GaussianProcessRegressor.minus_inf_value, read at call
  * time by the reference: gpr.py:1145, 1201; gp_acquisition.py:788-792 changes it temporarily). */
 int gpry_set_mask_value(gpry_state* st, double value);
