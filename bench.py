@@ -48,7 +48,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-secondary", action="store_true")
-    p.add_argument("--contract", choices=("fp64", "int8"), default="fp64",
+    p.add_argument("--contract", choices=("fp64", "int8"), default="int8",
                    help="variance contraction: FP64 DMMA or the exact INT8 split (tcgen05)")
     return p.parse_args()
 

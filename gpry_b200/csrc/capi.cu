@@ -6,6 +6,8 @@
 
 #include "state.cuh"
 
+#include <cstdlib>
+
 namespace gpry {
 
 static thread_local std::string g_last_error;
@@ -154,6 +156,8 @@ int gpry_state_create(int device, gpry_state** out) {
     gpry_state* st = new gpry_state();
     st->device = device;
     st->n_sm = p.multiProcessorCount;
+    if (const char* e = getenv("GPRY_B200_CONTRACT"))      // "fp64" / "int8": A/B switch
+      st->contract_mode = (std::string(e) == "fp64") ? GPRY_CONTRACT_FP64 : GPRY_CONTRACT_INT8;
     *out = st;
   });
 }

@@ -297,11 +297,12 @@ size_t ozaki_kslices_bytes(const gpry_state* st, int tiles) {
   return (size_t)tiles * (st->Npad / OZ_KC) * OZ_NS * OZ_A_BYTES;
 }
 
-// ssqp[split][chunk_cands] for `tiles` candidate tiles whose digits are in st->oz_Ksl
-void ozaki_contract(gpry_state* st, int tiles, int chunk_cands, cudaStream_t s) {
+// ssqp[split][chunk_cands] for `tiles` candidate tiles whose digits are in Ksl
+void ozaki_contract(gpry_state* st, const uint8_t* Ksl, int tiles, int chunk_cands,
+                    cudaStream_t s) {
   dim3 grid(st->oz_splits, tiles);
   oz_contract_kernel<<<grid, OZ_THREADS, OZ_SMEM, s>>>(
-      st->oz_Ksl.p, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p,
+      Ksl, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p,
       st->oz_rb.p + (size_t)st->oz_splits * st->oz_max_rb, st->oz_max_rb, st->ssqp.p, chunk_cands);
   GPRY_CUDA(cudaGetLastError());
 }

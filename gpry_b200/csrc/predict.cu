@@ -233,6 +233,8 @@ __device__ __forceinline__ void finish_one(const FinishParams& f, int i, bool ha
   if (isnan(m_)) mean = m_;
   if (f.o_mean) f.o_mean[i] = mean;
   if (have_var) {
+    if (isnan(m_)) ssq = m_;                      // a NaN in k* reaches every output (INT8 digits
+                                                  // of a NaN are meaningless, the FP64 sum is not)
     double var = f.c - ssq;                       // gpr.py:1207-1208
     if (var < 0.0) var = 0.0;                     // :1214-1219
     double sd = sqrt(var) * f.y_std;              // :1220, preprocessing.py:630
@@ -686,7 +688,7 @@ static void launch_build(gpry_state* st, const double* dX, int64_t M, int64_t ca
   const int NJ = st->Npad / JS;
   const int d = st->d, DP = st->DP;
   dim3 grid(tiles, JS), block(128);
-  void* kout = WMODE == 2 ? (void*)st->oz_Ksl.p : (void*)st->Ks.p;
+  void* kout = WMODE == 2 ? (void*)st->oz_Ksl_cur : (void*)st->Ks.p;
   const double slice_scale = 18014398509481984.0 / st->c;   // 2^54 / c
   if (d <= MAX_DIM_REG) {
     size_t smem = ((size_t)NJ * DP + NJ + 128 * d + (d & 1)) * 8 + 16;
@@ -697,7 +699,7 @@ static void launch_build(gpry_state* st, const double* dX, int64_t M, int64_t ca
       GPRY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                      (int)smem));                                             \
     kern<<<grid, block, smem, s>>>(dX, M, d, cand0, st->T.p, st->alpha.p, NJ, st->nKT, st->c, \
-                                   st->prm, kout, st->meanp.p, chunk_cands, slice_scale);     \
+                                   st->prm, kout, st->meanp_cur, chunk_cands, slice_scale);   \
   } break;
     switch (DP) {
       GPRY_LAUNCH_BUILD(4)
@@ -718,7 +720,7 @@ static void launch_build(gpry_state* st, const double* dX, int64_t M, int64_t ca
     auto kern = kstar_build_generic_kernel<KIND, WMODE == 1>;
     GPRY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, block, smem, s>>>(dX, M, d, DP, cand0, st->T.p, st->alpha.p, NJ, st->nKT, st->c,
-                                   st->prm_dev.p, st->Ks.p, st->meanp.p, chunk_cands);
+                                   st->prm_dev.p, st->Ks.p, st->meanp_cur, chunk_cands);
   }
   GPRY_CUDA(cudaGetLastError());
 }
@@ -980,13 +982,18 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
     st->Ks.reserve((size_t)chunk_tiles * st->nKT * TILE_DOUBLES);
   st->meanp.reserve((size_t)JS * chunk_cands);
   if (want_var) st->ssqp.reserve((size_t)row_splits * chunk_cands);
-  if (want_var)
+  if (want_var && !ozaki)
     GPRY_CUDA(cudaFuncSetAttribute(var_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(VcSmem)));
+  // (Running the K* build of chunk c+1 on a second stream under the INT8 contraction of chunk c
+  // was measured: the two kernels do co-reside, but the build's shared-memory reads slow the
+  // MMA operand fetch by as much as the overlap hides -- +1 % in total; not kept.)
   for (int64_t t0 = 0; t0 < total_tiles; t0 += chunk_tiles) {
     const int tiles = (int)std::min<int64_t>(chunk_tiles, total_tiles - t0);
     const int64_t cand0 = t0 * TILE_ROWS;
     const int n = (int)std::min<int64_t>((int64_t)tiles * TILE_ROWS, M - cand0);
+    st->meanp_cur = st->meanp.p;
+    st->oz_Ksl_cur = st->oz_Ksl.p;
     {
       TimedScope ts(st, s, T_BUILD);
       if (!want_var)
@@ -997,7 +1004,7 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
         launch_build_kind<1>(st, dX, M, cand0, tiles, JS, chunk_cands, s);
     }
     FinishParams fin;
-    fin.meanp = st->meanp.p;
+    fin.meanp = st->meanp_cur;
     fin.JS = JS;
     fin.chunk_cands = chunk_cands;
     fin.n_valid = n;
@@ -1011,7 +1018,7 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
     if (ozaki) {
       TimedScope ts(st, s, T_CONTRACT);
       st->n_contract_launches += 1;
-      ozaki_contract(st, tiles, chunk_cands, s);
+      ozaki_contract(st, st->oz_Ksl_cur, tiles, chunk_cands, s);
     } else if (want_var) {
       TimedScope ts(st, s, T_CONTRACT);
       st->n_contract_launches += 1;

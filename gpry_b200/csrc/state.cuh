@@ -72,12 +72,14 @@ struct gpry_state {
   // optional trust region applied to the mean on the device (gpr.py:1104-1109, 1200-1201)
   bool has_V = true;                     // false: mean-only state (classifier)
   // INT8 split of the variance contraction (ozaki.cu); contract_mode: 0 = FP64 DMMA, 1 = INT8
-  int contract_mode = 0;
+  int contract_mode = 1;
   bool oz_valid = false;                 // digits of V / row scales / split lists are current
   int oz_splits = 1, oz_max_rb = 0;
   gpry::DevBuf<uint8_t> oz_Ksl, oz_Vs;   // digits of the K* chunk / of V
   gpry::DevBuf<double> oz_scale;         // [Npad] c 2^e_j 2^-12, then [Npad] 2^e_j
   gpry::DevBuf<int> oz_rb;               // row blocks per split + counts
+  uint8_t* oz_Ksl_cur = nullptr;         // outputs of the build launch in flight
+  double* meanp_cur = nullptr;
   gpry_state* clf = nullptr;             // infinities classifier: a mean-only sub-state whose
   bool clf_on = false;                   //   'mean' is the SVC decision function (svm.py:308-346)
   gpry::DevBuf<double> clf_dec;          // decision values of the current call
@@ -175,7 +177,7 @@ void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_tr
 bool ozaki_supported(const gpry_state* st);
 void ozaki_prepare(gpry_state* st, cudaStream_t s);
 size_t ozaki_kslices_bytes(const gpry_state* st, int tiles);
-void ozaki_contract(gpry_state* st, int tiles, int chunk_cands, cudaStream_t s);
+void ozaki_contract(gpry_state* st, const uint8_t* Ksl, int tiles, int chunk_cands, cudaStream_t s);
 void factor_download_device(gpry_state* st, double* out_L, double* out_V);
 void lml_batched_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                         const double* noise2, const double* y_t, const double* thetas, int B,

@@ -95,8 +95,8 @@ class DeviceGP:
         self.N, self.d, self.kind = self._f_N, d, self._f_kind
 
     def set_contract_mode(self, mode):
-        """"fp64" (DMMA, default) or "int8" (exact 7-digit integer split on the INT8 tensor
-        cores) for the variance contraction of large pools."""
+        """"int8" (exact 7-digit integer split on the INT8 tensor cores, default) or "fp64"
+        (DMMA) for the variance contraction of large pools."""
         check(self._lib.gpry_set_contract_mode(self._h, {"fp64": 0, "int8": 1}[mode]))
 
     def set_mask_value(self, value):

@@ -112,13 +112,14 @@ int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const doub
 
 /*
  * How the variance contraction sum_j (sum_k V_jk k*_ik)^2 of gpr.py:1204-1208 is evaluated:
- *   GPRY_CONTRACT_FP64 (default)  FP64 tensor cores (DMMA.8x8x4)
- *   GPRY_CONTRACT_INT8            exact integer split of both operands into 7 int8 digits, 28
+ *   GPRY_CONTRACT_FP64            FP64 tensor cores (DMMA.8x8x4)
+ *   GPRY_CONTRACT_INT8 (default)  exact integer split of both operands into 7 int8 digits, 28
  *                                 digit products on the INT8 tensor cores (tcgen05.mma kind::i8,
  *                                 int32 accumulators in TMEM), recombined in FP64; same result
  *                                 to within the rounding error of an FP64 dot product.  Used for
  *                                 512 <= N_pad <= 16384, d <= 32 and more than 64 candidates per
- *                                 call; other calls silently use FP64.
+ *                                 call; other calls use FP64.  The environment variable
+ *                                 GPRY_B200_CONTRACT=fp64|int8 sets the initial mode of new states.
  */
 #define GPRY_CONTRACT_FP64 0
 #define GPRY_CONTRACT_INT8 1

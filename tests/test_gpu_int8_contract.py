@@ -1,0 +1,124 @@
+"""The INT8 split of the variance contraction (ozaki.cu) against the oracle, the committed
+golden vectors and the FP64 DMMA contraction, on models large enough to take that path
+(N_pad >= 512, d <= 32, more than 64 candidates per call)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, oracle_state, scaled_err
+from oracle import gp_oracle as orc
+from test_gpu_predict import upload_from_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from gpry_b200 import DeviceGP
+    d = DeviceGP(0)
+    yield d
+    d.close()
+
+
+@pytest.mark.parametrize("name", ["rbf_d12_n500_c4", "rbf_d8_n1000"])
+def test_int8_matches_golden_and_fp64(dev, name):
+    g = load_golden(name)
+    st = oracle_state(g)
+    upload_from_oracle(dev, st)
+    sy = float(g["y_std"])
+    Xc = np.resize(g["Xc"], (max(len(g["Xc"]), 700), g["d"]))        # > 64 rows: tiled path
+    n = len(g["Xc"])
+    out = {}
+    for mode in ("fp64", "int8"):
+        dev.set_contract_mode(mode)
+        out[mode] = dev.predict_logexp(Xc, float(g["zeta"]), float(g["noise_level"]), st.y_max)
+    dev.set_contract_mode("int8")
+    for mode in ("fp64", "int8"):
+        mean, std, acq = out[mode]
+        assert scaled_err(mean[:n], g["mean"], sy) < TOL
+        assert scaled_err(std[:n] ** 2, g["std"] ** 2, sy ** 2) < TOL
+    assert np.array_equal(out["fp64"][0], out["int8"][0])              # the mean is not touched
+    assert scaled_err(out["int8"][1] ** 2, out["fp64"][1] ** 2, sy ** 2) < 1e-12
+    # ranking through the fused call: same survivors, same order
+    a8, i8, *_ = dev.predict_logexp_topk(Xc[:n], float(g["zeta"]), float(g["noise_level"]),
+                                         st.y_max, 64)
+    dev.set_contract_mode("fp64")
+    a64, i64, *_ = dev.predict_logexp_topk(Xc[:n], float(g["zeta"]), float(g["noise_level"]),
+                                           st.y_max, 64)
+    dev.set_contract_mode("int8")
+    resolved = np.abs(np.diff(a64)) > 1e-9            # ties closer than the tolerance may swap
+    assert np.array_equal(i8[:-1][resolved], i64[:-1][resolved])
+
+
+@pytest.mark.parametrize("kind,N,d", [("rbf", 513, 3), ("matern15", 1100, 7), ("matern25", 2000, 12),
+                                      ("rbf", 3000, 32)])
+def test_int8_ragged_sizes_vs_oracle(dev, kind, N, d):
+    X, y, theta, bounds = orc.synthetic_problem(N, d)
+    st = orc.GPState(kind, theta, X, y, bounds=bounds)
+    upload_from_oracle(dev, st)
+    dev.set_contract_mode("int8")
+    rng = np.random.default_rng(N)
+    for M in (65, 129, 1000, 40000):
+        Xc = rng.uniform(size=(M, d))
+        mean, std = dev.predict(Xc, return_std=True)
+        pick = np.unique(np.concatenate([np.arange(min(M, 40)), np.arange(max(M - 40, 0), M)]))
+        mo, so = orc.predict(st, Xc[pick], return_std=True)
+        assert scaled_err(mean[pick], mo, st.y_std) < TOL
+        assert scaled_err(std[pick] ** 2, so ** 2, st.y_std ** 2) < TOL
+        # chunk / order independence of the integer path: bit-identical under permutation
+        perm = rng.permutation(M)
+        m2, s2 = dev.predict(np.ascontiguousarray(Xc[perm]), return_std=True)
+        assert np.array_equal(m2, mean[perm]) and np.array_equal(s2, std[perm])
+    # training points: tiny variances, clamp at zero, never NaN
+    Xt = X[:200]
+    mean, std = dev.predict(Xt, return_std=True)
+    mo, so = orc.predict(st, Xt, return_std=True)
+    assert np.all(np.isfinite(std)) and np.all(std >= 0)
+    assert scaled_err(std ** 2, so ** 2, st.y_std ** 2) < TOL
+
+
+def test_int8_nonfinite_and_extreme_scales(dev):
+    # wide dynamic range in V (small noise -> entries of L^-1 up to ~1e4) and a large constant c
+    N, d = 640, 2
+    X, y, theta, bounds = orc.synthetic_problem(N, d)
+    theta = theta.copy()
+    theta[0] = np.log(1e4)
+    st = orc.GPState("rbf", theta, X, y, bounds=bounds, noise_level=1e-4)
+    upload_from_oracle(dev, st)
+    rng = np.random.default_rng(5)
+    Xc = rng.uniform(size=(3000, d))
+    Xc[7, 1] = np.nan
+    Xc[11, 0] = np.inf
+    res = {}
+    for mode in ("fp64", "int8"):
+        dev.set_contract_mode(mode)
+        res[mode] = dev.predict_logexp(Xc, 0.3, st.noise_level, st.y_max)
+    dev.set_contract_mode("int8")
+    m8, s8, a8 = res["int8"]
+    m64, s64, a64 = res["fp64"]
+    assert np.isnan(m8[7]) and np.isnan(s8[7]) and np.isnan(a8[7])
+    assert np.isfinite(s8[11]) and s8[11] == s64[11]            # k* = 0 everywhere: var = c
+    good = np.ones(len(Xc), bool)
+    good[[7, 11]] = False
+    mo, so = orc.predict(st, Xc[good][:600], return_std=True)
+    # ill-conditioned (cond(K) >> 1e10): compare both device paths with the oracle on equal
+    # footing -- the integer path must be as close to it as the FP64 path is (or within 1e-10)
+    c = float(np.exp(theta[0]))
+    err64 = np.max(np.abs(s64[good][:600] ** 2 - so ** 2)) / (c * st.y_std ** 2)
+    err8 = np.max(np.abs(s8[good][:600] ** 2 - so ** 2)) / (c * st.y_std ** 2)
+    assert err8 < max(1e-10, 4 * err64)
+
+
+def test_int8_used_only_where_supported(dev):
+    """Small models, wide models and small batches silently take the FP64 path: same numbers
+    whatever the mode."""
+    for N, d, M in [(300, 4, 500), (600, 40, 500), (600, 4, 64)]:
+        X, y, theta, bounds = orc.synthetic_problem(N, d)
+        st = orc.GPState("rbf", theta, X, y, bounds=bounds)
+        upload_from_oracle(dev, st)
+        Xc = np.random.default_rng(1).uniform(size=(M, d))
+        dev.set_contract_mode("fp64")
+        a = dev.predict(Xc, return_std=True)
+        dev.set_contract_mode("int8")
+        b = dev.predict(Xc, return_std=True)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
