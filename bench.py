@@ -7,7 +7,8 @@ ConstantKernel x RBF at fixed theta, 12.5e6 synthetic candidates PER GPU (weak s
 8 GPUs -> 10^8), K' = 1024 survivors per GPU merged through an NCCL all-gather.
 
 One step = one pass of the hot path over the rank's candidate pool:
-    K* build -> variance contraction (FP64 DMMA) -> finish/LogExp -> top-K' -> all-gather+merge.
+    K* build -> variance contraction (exact INT8 split on tcgen05, or FP64 DMMA with
+    --contract fp64) -> finish/LogExp -> top-K' -> all-gather+merge.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA, sm_100a)
   python bench.py --impl reference ...                         reference arm: the CPU port of
@@ -472,23 +473,46 @@ def run_ours(args):
         del a, b
     except Exception:
         pass
+    int8 = args.contract == "int8" and N > 384 and d <= 32      # the library's own criterion
+    prof_name = "r01_oz_contract_ncu.json" if int8 else "r01_contract_ncu.json"
     traffic, traffic_src = None, None
     try:   # dram bytes per launch of the same kernel from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r01_contract_ncu.json")) as f:
+        with open(os.path.join(ROOT, "profiles", prof_name)) as f:
             prof = json.load(f)
         if N == 2000 and d == 12:
             traffic = prof["traffic_bytes_per_launch"] * (cands_per_launch / (296 * 128))
             traffic_src = prof["source"]
     except Exception:
         pass
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_src,
-                "kernel": "var_contract_kernel (FP64 DMMA.8x8x4)",
-                "flop_per_candidate": flop_per_cand,
-                "ms_per_launch": contract_ms_per_launch,
-                "stage_ms_per_step": {k: tm[k] / args.steps for k in
-                                      ("build_ms", "contract_ms", "finish_ms", "topk_ms")}}
+    stage_ms = {k: tm[k] / args.steps for k in ("build_ms", "contract_ms", "finish_ms", "topk_ms")}
+    if int8:
+        # The contraction runs on the INT8 tensor pipe: each FP64 multiply-add of the algorithm
+        # costs 28 int8 multiply-adds (7 x 7 digit products with p + q <= 6), so the pipe's
+        # measured rate / 28 is the ceiling in algorithmic FP64 flop/s.
+        int8_peak = dev.int8_peak_tops()
+        pairs = 28
+        rows_pad = -(-N // 64) * 64
+        executed = pairs * 2.0 * 128 * 64 * 32 * sum(2 * (rb + 1) for rb in range(rows_pad // 64)) / 128
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": int8_peak / pairs,
+                    "unit": "TFLOP/s", "frac": achieved / (int8_peak / pairs), "traffic": traffic,
+                    "traffic_source": traffic_src,
+                    "peak_source": "tcgen05.mma kind::i8 128x256x32 issue rate measured in this run "
+                                   f"({int8_peak:.0f} TOPS) / 28 int8 products per FP64 product",
+                    "kernel": "oz_contract_kernel (exact INT8 split, tcgen05.mma kind::i8, TMEM)",
+                    "flop_per_candidate": flop_per_cand,
+                    "int8_tops_executed": executed * cands_per_launch
+                    / (contract_ms_per_launch * 1e-3) * 1e-12,
+                    "int8_tops_peak": int8_peak,
+                    "fp64_dgemm_tflops": peak, "fp64_dgemm_source": peak_src,
+                    "vs_fp64_tensor_peak": achieved / peak,
+                    "ms_per_launch": contract_ms_per_launch, "stage_ms_per_step": stage_ms}
+    else:
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src,
+                    "kernel": "var_contract_kernel (FP64 DMMA.8x8x4)",
+                    "flop_per_candidate": flop_per_cand,
+                    "ms_per_launch": contract_ms_per_launch, "stage_ms_per_step": stage_ms}
 
     # ---- every rank checks a sample of ITS OWN shard against the oracle (first / middle / last
     # tiles), max error reduced over ranks ----
@@ -559,7 +583,8 @@ def run_ours(args):
                                    f"top-{Kp}, N_train={N}, d={d}, RBF, {M} candidates/GPU",
                        "candidates_per_gpu": M, "candidates_total": world * M, "n_train": N,
                        "dim": d, "kprime": Kp, "parallelism": f"candidate-sharded x{world}",
-                       "l2": "inputs (1.2 GB/GPU) and K* scratch (>600 MB) exceed the 126 MB L2",
+                       "contraction": args.contract,
+                       "l2": "inputs (1.2 GB/GPU) and K* scratch (>500 MB) exceed the 126 MB L2",
                        "state_bcast_ms": t_bcast_ms},
             "e2e": e2e, "gpu_launches": int(tm["launches"]), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "agreement": agreement, "clocks": clk,

@@ -39,6 +39,7 @@ SIGNATURES = {
     "gpry_predict_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "gpry_set_contract_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "gpry_int8_peak": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gpry_set_mask_value": (C.c_int, [C.c_void_p, C.c_double]),
     "gpry_set_classifier": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_double, C.c_double]),

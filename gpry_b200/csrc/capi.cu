@@ -247,6 +247,13 @@ int gpry_set_contract_mode(gpry_state* st, int mode) {
   });
 }
 
+int gpry_int8_peak(gpry_state* st, double* out_tops) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr && out_tops != nullptr, "NULL argument");
+    *out_tops = ozaki_int8_peak_tops(st);
+  });
+}
+
 int gpry_set_mask_value(gpry_state* st, double value) {
   return guarded([&] {
     GPRY_CHECK_ARG(st != nullptr, "state is NULL");

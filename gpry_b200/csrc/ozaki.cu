@@ -241,7 +241,90 @@ __global__ void oz_row_scale_kernel(const double* __restrict__ row_pow2, int Np,
   if (j < Np) row_scale[j] = c * row_pow2[j] * 0.000244140625;
 }
 
+// ---------------------------------------------------------------------------------------
+// Roofline denominator: issue rate of tcgen05.mma kind::i8 at its best shape (128 x 256 x 32)
+// on operands resident in shared memory, every SM busy.  No memory traffic, no epilogue.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t OZ_IDESC_PEAK = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+__global__ void __launch_bounds__(128, 1) oz_peak_kernel(int reps) {
+  extern __shared__ __align__(1024) uint8_t smem[];     // A: 4 x 4096, B: 4 x 8192 (values irrelevant)
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int e = tid; e < (4 * 4096 + 4 * 8192) / 16; e += 128)
+    reinterpret_cast<uint4*>(smem)[e] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  uint32_t phase = 0;
+  for (int r = 0; r < reps; r++) {
+    if (tid == 0) {
+      const uint64_t da0 = oz_desc(smem_u32(smem), 2048, 128);
+      const uint64_t db0 = oz_desc(smem_u32(smem) + 4 * 4096, 4096, 128);
+#pragma unroll
+      for (int p = 0; p < 16; p++) {
+#pragma unroll
+        for (int kc = 0; kc < 4; kc++)
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+              ::"r"(tmem + (uint32_t)((p & 1) * 256)), "l"(da0 + (uint64_t)((kc * 4096) >> 4)),
+              "l"(db0 + (uint64_t)((kc * 8192) >> 4)), "r"(OZ_IDESC_PEAK), "r"(kc > 0 ? 1u : 0u), "r"(0u)
+              : "memory");
+      }
+      oz_commit(&bar);
+    }
+    oz_wait(&bar, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u)
+                 : "memory");
+}
+
 }  // namespace
+
+double ozaki_int8_peak_tops(gpry_state* st) {
+  GPRY_CUDA(cudaSetDevice(st->device));
+  const size_t smem = 4 * 4096 + 4 * 8192;
+  GPRY_CUDA(cudaFuncSetAttribute(oz_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  cudaEvent_t e0, e1;
+  GPRY_CUDA(cudaEventCreate(&e0));
+  GPRY_CUDA(cudaEventCreate(&e1));
+  const int reps = 400;
+  oz_peak_kernel<<<st->n_sm, 128, smem>>>(20);
+  float best = 1e30f;
+  for (int t = 0; t < 3; t++) {
+    GPRY_CUDA(cudaEventRecord(e0));
+    oz_peak_kernel<<<st->n_sm, 128, smem>>>(reps);
+    GPRY_CUDA(cudaEventRecord(e1));
+    GPRY_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    GPRY_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+  }
+  GPRY_CUDA(cudaGetLastError());
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double ops = 2.0 * (double)st->n_sm * reps * 16 * 4 * 128.0 * 256.0 * 32.0;
+  return ops / (best * 1e-3) * 1e-12;
+}
 
 bool ozaki_supported(const gpry_state* st) {
   return st->has_V && st->d <= MAX_DIM_REG && st->Npad >= 512 && st->Npad <= 16384;

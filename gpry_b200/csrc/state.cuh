@@ -175,6 +175,7 @@ void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_tr
                       double* out_L, double* out_V, double* out_alpha, double* out_logdet_half,
                       int* info, bool keep);
 bool ozaki_supported(const gpry_state* st);
+double ozaki_int8_peak_tops(gpry_state* st);
 void ozaki_prepare(gpry_state* st, cudaStream_t s);
 size_t ozaki_kslices_bytes(const gpry_state* st, int tiles);
 void ozaki_contract(gpry_state* st, const uint8_t* Ksl, int tiles, int chunk_cands, cudaStream_t s);

@@ -99,6 +99,12 @@ class DeviceGP:
         (DMMA) for the variance contraction of large pools."""
         check(self._lib.gpry_set_contract_mode(self._h, {"fp64": 0, "int8": 1}[mode]))
 
+    def int8_peak_tops(self):
+        """Measured tcgen05 INT8 MMA issue rate of this GPU (TOPS): roofline denominator."""
+        out = C.c_double(0.0)
+        check(self._lib.gpry_int8_peak(self._h, C.byref(out)))
+        return out.value
+
     def set_mask_value(self, value):
         """The value masked rows get for the mean (``minus_inf_value``)."""
         check(self._lib.gpry_set_mask_value(self._h, float(value)))

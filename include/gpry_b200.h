@@ -125,6 +125,11 @@ int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const doub
 #define GPRY_CONTRACT_INT8 1
 int gpry_set_contract_mode(gpry_state* st, int mode);
 
+/* Measured issue rate (TOPS, 2 ops per multiply-add) of tcgen05.mma kind::i8 at its best shape
+ * (128 x 256 x 32) on operands resident in shared memory, all SMs busy: the roofline
+ * denominator of the INT8 contraction.  Takes a few milliseconds. */
+int gpry_int8_peak(gpry_state* st, double* out_tops);
+
 /* The value written by the two masks (GaussianProcessRegressor.minus_inf_value, read at call
  * time by the reference: gpr.py:1145, 1201; gp_acquisition.py:788-792 changes it temporarily). */
 int gpry_set_mask_value(gpry_state* st, double value);
