@@ -188,6 +188,10 @@ class GaussianProcessRegressor:
 
     def __setstate__(self, state):
         self.__dict__.update(state)
+        if "LOCAL_RANK" in os.environ:
+            # device ordinals are per process: a regressor broadcast from another rank
+            # (mpi.bcast of the reference, gp_acquisition.py:453) must use this rank's GPU
+            self.device = default_device()
         self._dev = None
         self._dev_dirty = True
         self._factor_resident = False

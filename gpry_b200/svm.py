@@ -156,6 +156,12 @@ class SVM:
         state["_dev_dirty"] = True
         return state
 
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        import os
+        if "LOCAL_RANK" in os.environ:
+            self.device = None       # device ordinals are per process: use this rank's GPU
+
     def __deepcopy__(self, memo):
         from copy import deepcopy
         new = self.__class__.__new__(self.__class__)

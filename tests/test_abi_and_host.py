@@ -156,6 +156,24 @@ def test_gpr_host_logic_without_gpu():
     assert deepcopy(gpr).kernel == gpr.kernel
 
 
+def test_unpickled_regressor_uses_the_local_gpu(monkeypatch):
+    """A regressor broadcast from another rank (the reference's mpi.bcast of the GPR,
+    gp_acquisition.py:453) must run on the receiving process's GPU: device ordinals are per
+    process, one process per GPU (LOCAL_RANK)."""
+    import pickle
+    from gpry_b200.gpr import GaussianProcessRegressor
+    from gpry_b200.svm import SVM
+    bounds = np.array([[0.0, 1.0]] * 3)
+    gpr = GaussianProcessRegressor(bounds=bounds, verbose=0, device=0, account_for_inf="SVM")
+    blob = pickle.dumps(gpr)
+    assert pickle.loads(blob).device == 0                 # single process: kept
+    monkeypatch.setenv("LOCAL_RANK", "1")
+    g2 = pickle.loads(blob)
+    assert g2.device == 1 and isinstance(g2.infinities_classifier, SVM)
+    assert g2.infinities_classifier.device is None
+    assert deepcopy(g2).device == 1
+
+
 def test_lockstep_restart_driver_without_gpu():
     """The lock-step multi-restart driver (one batched objective call per round) reaches the
     optima a serial L-BFGS-B reaches, and propagates a failing evaluation instead of hanging."""

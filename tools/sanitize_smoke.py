@@ -8,7 +8,7 @@ from gpry_b200 import DeviceGP
 from test_gpu_predict import upload_from_oracle
 
 dev = DeviceGP(0)
-for kind, N, d, M in [("rbf", 300, 5, 700), ("matern25", 140, 33, 130)]:
+for kind, N, d, M in [("rbf", 300, 5, 700), ("matern25", 140, 33, 130), ("rbf", 700, 6, 900)]:   # the last one takes the INT8 contraction
     X, y, theta, bounds = orc.synthetic_problem(N, d)
     st = orc.GPState(kind, theta, X, y, bounds=bounds)
     upload_from_oracle(dev, st)
