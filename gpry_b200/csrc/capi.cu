@@ -157,7 +157,9 @@ int gpry_state_create(int device, gpry_state** out) {
     st->device = device;
     st->n_sm = p.multiProcessorCount;
     if (const char* e = getenv("GPRY_B200_CONTRACT"))      // "fp64" / "int8": A/B switch
-      st->contract_mode = (std::string(e) == "fp64") ? GPRY_CONTRACT_FP64 : GPRY_CONTRACT_INT8;
+      st->contract_mode = (std::string(e) == "fp64") ? GPRY_CONTRACT_FP64
+                          : (std::string(e) == "int8_1pass") ? GPRY_CONTRACT_INT8_1PASS
+                                                             : GPRY_CONTRACT_INT8;
     *out = st;
   });
 }
@@ -178,7 +180,7 @@ int gpry_state_destroy(gpry_state* st) {
     st->tmp.release(); st->small.release(); st->Vrm.release(); st->trust.release();
     st->pc_U.release(); st->pc_Ks.release(); st->pc_UT.release(); st->pc_G.release();
     st->VTrm.release(); st->gr_out.release(); st->clf_dec.release();
-    st->oz_Ksl.release(); st->oz_Vs.release(); st->oz_scale.release(); st->oz_rb.release();
+    st->oz_Ksl.release(); st->oz_Vs.release(); st->oz_scale.release(); st->oz_rb.release(); st->oz_park.release();
     if (st->clf) gpry_state_destroy(st->clf);
     st->f_K.release(); st->f_VT.release(); st->f_W.release(); st->f_TT.release();
     st->f_Winv.release(); st->f_misc.release(); st->f_prob.release();
@@ -242,7 +244,7 @@ int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const doub
 int gpry_set_contract_mode(gpry_state* st, int mode) {
   return guarded([&] {
     GPRY_CHECK_ARG(st != nullptr, "state is NULL");
-    GPRY_CHECK_ARG(mode == GPRY_CONTRACT_FP64 || mode == GPRY_CONTRACT_INT8, "unknown mode");
+    GPRY_CHECK_ARG(mode >= GPRY_CONTRACT_FP64 && mode <= GPRY_CONTRACT_INT8_1PASS, "unknown mode");
     st->contract_mode = mode;
   });
 }

@@ -20,6 +20,7 @@
 #include "state.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 namespace gpry {
@@ -184,6 +185,190 @@ oz_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__ 
                  : "memory");
 }
 
+// ---------------------------------------------------------------------------------------
+// Two-pass variant with 128 x 128 x 32 MMAs (1.5x the issue rate of the 128 x 64 shape).
+// Only 4 accumulators of 128 columns fit in TMEM, so the digit groups of a 128-row block of V are
+// produced in two passes over its k range:
+//   pass 1: groups 0..3 (10 products, digits 0..3 of both operands)  -> hi = sum_{g<=3} 256^-g S_g,
+//           exact in FP64, parked in an L2-resident scratch line of this SM (128 x 128 doubles)
+//   pass 2: groups 4..6 (18 products, all digits)                   -> lo = sum_{g=4..6} 256^(4-g) S_g
+//   row product = scale_j (hi + 2^-32 lo)
+// ---------------------------------------------------------------------------------------
+constexpr int OZ2_ROWS = 128;
+constexpr int OZ2_B_BYTES = OZ2_ROWS * OZ_KC;                        // 4096 per digit and chunk
+constexpr int OZ2_STAGE_BYTES = OZ_NS * (OZ_A_BYTES + OZ2_B_BYTES);  // 57344
+constexpr int OZ2_STAGES = 4;                                        // 224 KB
+constexpr size_t OZ2_SMEM = (size_t)OZ2_STAGES * OZ2_STAGE_BYTES + 256;
+constexpr int OZ2_PARK_SLOTS = 256;                                  // indexed by %smid
+constexpr uint32_t OZ2_IDESC = (2u << 4) | (1u << 7) | (1u << 10) |
+                               ((uint32_t)(OZ2_ROWS >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
+
+__device__ __forceinline__ void oz2_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(OZ2_IDESC), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__ Vs, int nKC,
+                    const double* __restrict__ row_scale, const int* __restrict__ rb_list,
+                    const int* __restrict__ rb_count, int max_rb, double* __restrict__ park,
+                    double* __restrict__ ssqp, int chunk_cands) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)OZ2_STAGES * OZ2_STAGE_BYTES);
+  uint64_t* empty = full + OZ2_STAGES;
+  uint64_t* tmem_full = empty + OZ2_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x, tile = blockIdx.y;
+  const int n_rb = rb_count[split];
+  const int* my_rb = rb_list + (size_t)split * max_rb;
+
+  if (tid == 0) {
+    for (int s = 0; s < OZ2_STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 128);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {   // ---- producer
+      const uint8_t* Abase = Ksl + (size_t)tile * nKC * (size_t)(OZ_NS * OZ_A_BYTES);
+      int it = 0;
+      for (int r = 0; r < n_rb; r++) {
+        const int rb = my_rb[r];
+        const uint8_t* Bbase = Vs + (size_t)rb * nKC * (size_t)(OZ_NS * OZ2_B_BYTES);
+        const int nch = 4 * (rb + 1);      // rows 128 rb .. +127 are zero beyond k = 128 (rb + 1)
+        for (int pass = 0; pass < 2; pass++) {
+          const uint32_t nd = pass == 0 ? 4u : (uint32_t)OZ_NS;      // digits of each operand needed
+          for (int kc = 0; kc < nch; kc++, it++) {
+            const int s = it % OZ2_STAGES;
+            oz_wait(&empty[s], ((it / OZ2_STAGES) & 1) ^ 1);
+            uint8_t* dst = smem + (size_t)s * OZ2_STAGE_BYTES;
+            mbar_expect_tx(&full[s], nd * (OZ_A_BYTES + OZ2_B_BYTES));
+            tma_bulk_g2s(dst, Abase + (size_t)kc * (OZ_NS * OZ_A_BYTES), nd * OZ_A_BYTES, &full[s]);
+            tma_bulk_g2s(dst + OZ_NS * OZ_A_BYTES, Bbase + (size_t)kc * (OZ_NS * OZ2_B_BYTES),
+                         nd * OZ2_B_BYTES, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {   // ---- MMA issuer
+      int it = 0, t = 0;
+      for (int r = 0; r < n_rb; r++) {
+        const int nch = 4 * (my_rb[r] + 1);
+        for (int pass = 0; pass < 2; pass++, t++) {
+          oz_wait(tmem_empty, (t & 1) ^ 1);        // the previous epilogue has drained TMEM
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int kc = 0; kc < nch; kc++, it++) {
+            const int s = it % OZ2_STAGES;
+            oz_wait(&full[s], (it / OZ2_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(smem + (size_t)s * OZ2_STAGE_BYTES);
+            const uint64_t da0 = oz_desc(sa, OZ_A_BYTES / 2, 128);
+            const uint64_t db0 = oz_desc(sa + OZ_NS * OZ_A_BYTES, OZ2_B_BYTES / 2, 128);
+            const uint32_t first = kc > 0 ? 1u : 0u;
+            if (pass == 0) {
+#pragma unroll
+              for (int g = 0; g < 4; g++) {
+#pragma unroll
+                for (int p = 0; p <= g; p++)
+                  oz2_mma(tmem + (uint32_t)(g * OZ2_ROWS), da0 + (uint64_t)((p * OZ_A_BYTES) >> 4),
+                          db0 + (uint64_t)(((g - p) * OZ2_B_BYTES) >> 4), p > 0 ? 1u : first);
+              }
+            } else {
+#pragma unroll
+              for (int g = 4; g < OZ_NS; g++) {
+#pragma unroll
+                for (int p = 0; p <= g; p++)
+                  oz2_mma(tmem + (uint32_t)((g - 4) * OZ2_ROWS), da0 + (uint64_t)((p * OZ_A_BYTES) >> 4),
+                          db0 + (uint64_t)(((g - p) * OZ2_B_BYTES) >> 4), p > 0 ? 1u : first);
+              }
+            }
+            oz_commit(&empty[s]);
+          }
+          oz_commit(tmem_full);
+        }
+      }
+    }
+  } else {
+    // ---- epilogue: thread = candidate (TMEM lane); 128 columns = rows of V
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    double* my_park = park + ((size_t)(smid % OZ2_PARK_SLOTS) * OZ2_ROWS) * TILE_ROWS + tid;
+    double ssq = 0.0;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    int t = 0;
+    for (int r = 0; r < n_rb; r++) {
+      const int rb = my_rb[r];
+      // pass 1: hi = S0 + S1/256 + S2/256^2 + S3/256^3 (exact), parked per (column, candidate)
+      oz_wait(tmem_full, t & 1);
+      t++;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int cc = 0; cc < OZ2_ROWS; cc += 16) {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int g = 0; g < 4; g++) OZ_TMEM_LD16(lane_base + (uint32_t)(g * OZ2_ROWS + cc), v[g]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          double hi = (double)(int)v[3][c];
+#pragma unroll
+          for (int g = 2; g >= 0; g--) hi = fma(hi, 0.00390625, (double)(int)v[g][c]);
+          my_park[(size_t)(cc + c) * TILE_ROWS] = hi;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      oz_arrive(tmem_empty);
+      // pass 2: lo = S4 + S5/256 + S6/256^2; row product = scale (hi + 2^-32 lo)
+      oz_wait(tmem_full, t & 1);
+      t++;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int cc = 0; cc < OZ2_ROWS; cc += 16) {
+        uint32_t v[3][16];
+#pragma unroll
+        for (int g = 0; g < 3; g++) OZ_TMEM_LD16(lane_base + (uint32_t)(g * OZ2_ROWS + cc), v[g]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          double lo = (double)(int)v[2][c];
+          lo = fma(lo, 0.00390625, (double)(int)v[1][c]);
+          lo = fma(lo, 0.00390625, (double)(int)v[0][c]);
+          const double acc = fma(lo, 2.3283064365386963e-10, my_park[(size_t)(cc + c) * TILE_ROWS]);
+          const double w = acc * __ldg(row_scale + rb * OZ2_ROWS + cc + c);
+          ssq = fma(w, w, ssq);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      oz_arrive(tmem_empty);
+    }
+    ssqp[(size_t)split * chunk_cands + tile * TILE_ROWS + tid] = ssq;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u)
+                 : "memory");
+}
+
 // per row of V (row-major, padded to Np): 2^e with |V_jk| / 2^e < 1
 __global__ void __launch_bounds__(256)
 oz_row_exponent_kernel(const double* __restrict__ Vrm, int Np, double* __restrict__ row_pow2) {
@@ -198,11 +383,11 @@ oz_row_exponent_kernel(const double* __restrict__ Vrm, int Np, double* __restric
     row_pow2[j] = ldexp(1.0, e);
   }
 }
-// digits of V: thread per (row j, 16 consecutive k); layout [row block of 64][k chunk of 32][slice]
-// [k16 (2)][row (64)][16 B]
+// digits of V: thread per (row j, 16 consecutive k); layout [row block][k chunk of 32][slice]
+// [k16 (2)][row in block][16 B], row blocks of 64 (one-pass kernel) or 128 (two-pass kernel)
 __global__ void __launch_bounds__(256)
 oz_slice_v_kernel(const double* __restrict__ Vrm, int Np, const double* __restrict__ row_pow2,
-                  uint8_t* __restrict__ Vs) {
+                  int rows_per_block, uint8_t* __restrict__ Vs) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n16 = Np / 16;
   if (e >= (int64_t)Np * n16) return;
@@ -227,11 +412,12 @@ oz_slice_v_kernel(const double* __restrict__ Vrm, int Np, const double* __restri
     packs[0][b >> 2] |= (uint32_t)((int)t & 0xFF) << (8 * (b & 3));
   }
   const int nKC = Np / OZ_KC;
-  uint8_t* base = Vs + ((size_t)(j / OZ_ROWS) * nKC + (k0 >> 5)) * (size_t)(OZ_NS * OZ_B_BYTES) +
-                  ((k0 >> 4) & 1) * (OZ_B_BYTES / 2) + (j % OZ_ROWS) * 16;
+  const int b_bytes = rows_per_block * OZ_KC;      // one digit of one chunk
+  uint8_t* base = Vs + ((size_t)(j / rows_per_block) * nKC + (k0 >> 5)) * (size_t)(OZ_NS * b_bytes) +
+                  ((k0 >> 4) & 1) * (b_bytes / 2) + (j % rows_per_block) * 16;
 #pragma unroll
   for (int p = 0; p < OZ_NS; p++)
-    *reinterpret_cast<uint4*>(base + p * OZ_B_BYTES) =
+    *reinterpret_cast<uint4*>(base + (size_t)p * b_bytes) =
         make_uint4(packs[p][0], packs[p][1], packs[p][2], packs[p][3]);
 }
 // row_scale[j] = c 2^e_j 2^-12
@@ -330,34 +516,50 @@ bool ozaki_supported(const gpry_state* st) {
   return st->has_V && st->d <= MAX_DIM_REG && st->Npad >= 512 && st->Npad <= 16384;
 }
 
-// digits of V and the balanced assignment of row blocks to row splits (once per upload)
+// digits of V and the balanced assignment of row blocks to row splits (once per upload and
+// variant: contract_mode 1 = two-pass 128-row blocks, 2 = one-pass 64-row blocks)
 void ozaki_prepare(gpry_state* st, cudaStream_t s) {
-  if (st->oz_valid) return;
-  const int Np = st->Npad, nRB = Np / OZ_ROWS, nKC = Np / OZ_KC;
-  st->oz_Vs.reserve((size_t)nRB * nKC * OZ_NS * OZ_B_BYTES);
+  const int rows = st->contract_mode == 2 ? OZ_ROWS : OZ2_ROWS;
+  if (st->oz_valid && st->oz_rows == rows) return;
+  const int Np = st->Npad, nRB = Np / rows, nKC = Np / OZ_KC;
+  st->oz_Vs.reserve((size_t)nRB * nKC * OZ_NS * rows * OZ_KC);
   st->oz_scale.reserve(2 * (size_t)Np);
   double* row_pow2 = st->oz_scale.p + Np;
   oz_row_exponent_kernel<<<(Np + 7) / 8, 256, 0, s>>>(st->Vrm.p, Np, row_pow2);
   GPRY_CUDA(cudaGetLastError());
   const int64_t tot = (int64_t)Np * (Np / 16);
-  oz_slice_v_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(st->Vrm.p, Np, row_pow2,
+  oz_slice_v_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(st->Vrm.p, Np, row_pow2, rows,
                                                                   st->oz_Vs.p);
   GPRY_CUDA(cudaGetLastError());
   oz_row_scale_kernel<<<(Np + 255) / 256, 256, 0, s>>>(row_pow2, Np, st->c, st->oz_scale.p);
   GPRY_CUDA(cudaGetLastError());
-  // row blocks beyond the last training row are all zero: skip them
-  const int used_rb = (st->N + OZ_ROWS - 1) / OZ_ROWS;
-  int splits = 1;
-  while (splits < 8 && splits * 2 <= used_rb) splits *= 2;
-  if (used_rb >= 12) splits = 6;       // 24 tiles x 6 splits fill 144 of 148 SMs per wave
-  std::vector<std::vector<int>> lists(splits);
-  std::vector<long long> load(splits, 0);
-  for (int rb = used_rb - 1; rb >= 0; rb--) {       // longest first, to the least loaded split
-    int best = 0;
-    for (int q = 1; q < splits; q++)
-      if (load[q] < load[best]) best = q;
-    lists[best].push_back(rb);
-    load[best] += rb + 1;
+  // Row blocks beyond the last training row are all zero: skip them.  Row splits: enough of
+  // them that the K* digits of the candidate tiles resident at one time (n_sm / splits tiles)
+  // stay in L2 (~40 MB), then the split count in that neighbourhood with the best balance.
+  const int used_rb = (st->N + rows - 1) / rows;
+  const double tile_mb = (double)nKC * OZ_NS * OZ_A_BYTES / 1048576.0;
+  int want = (int)std::ceil(st->n_sm * tile_mb / 40.0);
+  want = std::max(1, std::min(want, used_rb));
+  int splits = want;
+  double best_cost = 1e300;
+  std::vector<std::vector<int>> lists;
+  for (int cand = want; cand <= std::min(used_rb, want + 3); cand++) {
+    std::vector<std::vector<int>> l(cand);
+    std::vector<long long> load(cand, 0);
+    for (int rb = used_rb - 1; rb >= 0; rb--) {     // longest first, to the least loaded split
+      int b = 0;
+      for (int q = 1; q < cand; q++)
+        if (load[q] < load[b]) b = q;
+      l[b].push_back(rb);
+      load[b] += rb + 1;
+    }
+    const long long mx = *std::max_element(load.begin(), load.end());
+    const double cost = (double)mx * cand;          // makespan x CTAs ~ total SM time
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      splits = cand;
+      lists = l;
+    }
   }
   int max_rb = 0;
   for (auto& l : lists) max_rb = std::max(max_rb, (int)l.size());
@@ -368,11 +570,15 @@ void ozaki_prepare(gpry_state* st, cudaStream_t s) {
   }
   st->oz_rb.reserve(h.size());
   GPRY_CUDA(cudaMemcpyAsync(st->oz_rb.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  if (rows == OZ2_ROWS) st->oz_park.reserve((size_t)OZ2_PARK_SLOTS * OZ2_ROWS * TILE_ROWS);
   GPRY_CUDA(cudaStreamSynchronize(s));
   st->oz_splits = splits;
   st->oz_max_rb = max_rb;
+  st->oz_rows = rows;
   GPRY_CUDA(cudaFuncSetAttribute(oz_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)OZ_SMEM));
+  GPRY_CUDA(cudaFuncSetAttribute(oz2_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)OZ2_SMEM));
   st->oz_valid = true;
 }
 
@@ -384,9 +590,15 @@ size_t ozaki_kslices_bytes(const gpry_state* st, int tiles) {
 void ozaki_contract(gpry_state* st, const uint8_t* Ksl, int tiles, int chunk_cands,
                     cudaStream_t s) {
   dim3 grid(st->oz_splits, tiles);
-  oz_contract_kernel<<<grid, OZ_THREADS, OZ_SMEM, s>>>(
-      Ksl, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p,
-      st->oz_rb.p + (size_t)st->oz_splits * st->oz_max_rb, st->oz_max_rb, st->ssqp.p, chunk_cands);
+  const int* counts = st->oz_rb.p + (size_t)st->oz_splits * st->oz_max_rb;
+  if (st->oz_rows == OZ2_ROWS)
+    oz2_contract_kernel<<<grid, OZ_THREADS, OZ2_SMEM, s>>>(
+        Ksl, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p, counts, st->oz_max_rb,
+        st->oz_park.p, st->ssqp.p, chunk_cands);
+  else
+    oz_contract_kernel<<<grid, OZ_THREADS, OZ_SMEM, s>>>(
+        Ksl, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p, counts, st->oz_max_rb,
+        st->ssqp.p, chunk_cands);
   GPRY_CUDA(cudaGetLastError());
 }
 

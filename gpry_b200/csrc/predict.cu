@@ -965,7 +965,7 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
   const int chunk_tiles = (int)std::min<int64_t>(total_tiles, max_chunk_tiles);
   const int chunk_cands = chunk_tiles * TILE_ROWS;
   // INT8 split of the contraction (ozaki.cu) when selected and the model qualifies
-  const bool ozaki = want_var && st->contract_mode == 1 && ozaki_supported(st);
+  const bool ozaki = want_var && st->contract_mode != 0 && ozaki_supported(st);
   if (ozaki) ozaki_prepare(st, s);
   // row splits: for small pools spread the row blocks of V over more CTAs
   int row_splits = 1;

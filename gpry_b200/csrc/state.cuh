@@ -74,7 +74,8 @@ struct gpry_state {
   // INT8 split of the variance contraction (ozaki.cu); contract_mode: 0 = FP64 DMMA, 1 = INT8
   int contract_mode = 1;
   bool oz_valid = false;                 // digits of V / row scales / split lists are current
-  int oz_splits = 1, oz_max_rb = 0;
+  int oz_splits = 1, oz_max_rb = 0, oz_rows = 0;
+  gpry::DevBuf<double> oz_park;          // per-SM scratch of the two-pass kernel (L2 resident)
   gpry::DevBuf<uint8_t> oz_Ksl, oz_Vs;   // digits of the K* chunk / of V
   gpry::DevBuf<double> oz_scale;         // [Npad] c 2^e_j 2^-12, then [Npad] 2^e_j
   gpry::DevBuf<int> oz_rb;               // row blocks per split + counts

@@ -97,7 +97,7 @@ class DeviceGP:
     def set_contract_mode(self, mode):
         """"int8" (exact 7-digit integer split on the INT8 tensor cores, default) or "fp64"
         (DMMA) for the variance contraction of large pools."""
-        check(self._lib.gpry_set_contract_mode(self._h, {"fp64": 0, "int8": 1}[mode]))
+        check(self._lib.gpry_set_contract_mode(self._h, {"fp64": 0, "int8": 1, "int8_1pass": 2}[mode]))
 
     def int8_peak_tops(self):
         """Measured tcgen05 INT8 MMA issue rate of this GPU (TOPS): roofline denominator."""

@@ -122,7 +122,8 @@ int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const doub
  *                                 GPRY_B200_CONTRACT=fp64|int8 sets the initial mode of new states.
  */
 #define GPRY_CONTRACT_FP64 0
-#define GPRY_CONTRACT_INT8 1
+#define GPRY_CONTRACT_INT8 1       /* two passes over the digit groups, 128 x 128 x 32 MMAs */
+#define GPRY_CONTRACT_INT8_1PASS 2 /* one pass, 128 x 64 x 32 MMAs (all 7 groups in TMEM at once) */
 int gpry_set_contract_mode(gpry_state* st, int mode);
 
 /* Measured issue rate (TOPS, 2 ops per multiply-add) of tcgen05.mma kind::i8 at its best shape

@@ -16,7 +16,7 @@ for kind, N, d, M in [("rbf", 600, 5, 5000), ("rbf", 2000, 12, 2_000_000), ("mat
     Xd = torch.rand((M, d), dtype=torch.float64, device="cuda", generator=gen)
     out = {"kind": kind, "N": N, "d": d, "M": M}
     res = {}
-    for mode in ("fp64", "int8"):
+    for mode in ("fp64", "int8_1pass", "int8"):
         dev.set_contract_mode(mode)
         m, s = dev.predict(Xd, return_std=True)
         torch.cuda.synchronize()
@@ -31,7 +31,8 @@ for kind, N, d, M in [("rbf", 600, 5, 5000), ("rbf", 2000, 12, 2_000_000), ("mat
     out["var_diff_int8_vs_fp64"] = float(np.max(np.abs(res["fp64"][1] ** 2 - res["int8"][1] ** 2)) / sy ** 2)
     n = min(M, 3000)
     mo, so = orc.predict(st, Xd[:n].cpu().numpy(), return_std=True)
-    for mode in ("fp64", "int8"):
+    out["var_diff_1pass_vs_2pass"] = float(np.max(np.abs(res["int8_1pass"][1] ** 2 - res["int8"][1] ** 2)) / sy ** 2)
+    for mode in ("fp64", "int8_1pass", "int8"):
         out[f"var_err_{mode}_vs_oracle"] = float(np.max(np.abs(res[mode][1][:n] ** 2 - so ** 2)) / sy ** 2)
     print(json.dumps(out), flush=True)
 dev.close()
