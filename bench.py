@@ -491,14 +491,14 @@ def run_ours(args):
         # measured rate / 28 is the ceiling in algorithmic FP64 flop/s.
         int8_peak = dev.int8_peak_tops()
         pairs = 28
-        rows_pad = -(-N // 64) * 64
-        executed = pairs * 2.0 * 128 * 64 * 32 * sum(2 * (rb + 1) for rb in range(rows_pad // 64)) / 128
+        n_rb = -(-N // 128)          # 128-row blocks of V, k chunks of 32 up to the block's last row
+        executed = pairs * 2.0 * 128 * 128 * 32 * sum(4 * (rb + 1) for rb in range(n_rb)) / 128
         roofline = {"bound": "tensor", "achieved": achieved, "peak": int8_peak / pairs,
                     "unit": "TFLOP/s", "frac": achieved / (int8_peak / pairs), "traffic": traffic,
                     "traffic_source": traffic_src,
                     "peak_source": "tcgen05.mma kind::i8 128x256x32 issue rate measured in this run "
                                    f"({int8_peak:.0f} TOPS) / 28 int8 products per FP64 product",
-                    "kernel": "oz_contract_kernel (exact INT8 split, tcgen05.mma kind::i8, TMEM)",
+                    "kernel": "oz2_contract_kernel (exact INT8 split, two passes of 128x128x32 tcgen05.mma kind::i8, TMEM)",
                     "flop_per_candidate": flop_per_cand,
                     "int8_tops_executed": executed * cands_per_launch
                     / (contract_ms_per_launch * 1e-3) * 1e-12,

@@ -57,6 +57,11 @@ __device__ __forceinline__ void oz_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
   __trap();
 }
+// exact int32 -> double without the (quarter-rate) I2F.F64: the double with high word 0x43300000
+// and low word L is 2^52 + L; L = v + 2^31 (mod 2^32) for signed v
+__device__ __forceinline__ double oz_i2d(uint32_t v) {
+  return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
+}
 #define OZ_TMEM_LD16(taddr, r)                                                                   \
   asm volatile(                                                                                  \
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                  \
@@ -166,9 +171,9 @@ oz_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__ 
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int c = 0; c < 16; c++) {
-          double acc = (double)(int)v[OZ_NS - 1][c];
+          double acc = oz_i2d(v[OZ_NS - 1][c]);
 #pragma unroll
-          for (int g = OZ_NS - 2; g >= 0; g--) acc = fma(acc, 0.00390625, (double)(int)v[g][c]);
+          for (int g = OZ_NS - 2; g >= 0; g--) acc = fma(acc, 0.00390625, oz_i2d(v[g][c]));
           const double w = acc * __ldg(row_scale + rb * OZ_ROWS + cc + c);
           ssq = fma(w, w, ssq);
         }
@@ -195,6 +200,9 @@ oz_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__ 
 //   row product = scale_j (hi + 2^-32 lo)
 // ---------------------------------------------------------------------------------------
 constexpr int OZ2_ROWS = 128;
+#ifndef OZ2_EPI_COLS
+#define OZ2_EPI_COLS OZ2_ROWS   // (timing experiments only: fewer columns = shorter epilogue, wrong results)
+#endif
 constexpr int OZ2_B_BYTES = OZ2_ROWS * OZ_KC;                        // 4096 per digit and chunk
 constexpr int OZ2_STAGE_BYTES = OZ_NS * (OZ_A_BYTES + OZ2_B_BYTES);  // 57344
 constexpr int OZ2_STAGES = 4;                                        // 224 KB
@@ -322,16 +330,16 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
       t++;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cc = 0; cc < OZ2_ROWS; cc += 16) {
+      for (int cc = 0; cc < OZ2_EPI_COLS; cc += 16) {
         uint32_t v[4][16];
 #pragma unroll
         for (int g = 0; g < 4; g++) OZ_TMEM_LD16(lane_base + (uint32_t)(g * OZ2_ROWS + cc), v[g]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int c = 0; c < 16; c++) {
-          double hi = (double)(int)v[3][c];
+          double hi = oz_i2d(v[3][c]);
 #pragma unroll
-          for (int g = 2; g >= 0; g--) hi = fma(hi, 0.00390625, (double)(int)v[g][c]);
+          for (int g = 2; g >= 0; g--) hi = fma(hi, 0.00390625, oz_i2d(v[g][c]));
           my_park[(size_t)(cc + c) * TILE_ROWS] = hi;
         }
       }
@@ -342,16 +350,16 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
       t++;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cc = 0; cc < OZ2_ROWS; cc += 16) {
+      for (int cc = 0; cc < OZ2_EPI_COLS; cc += 16) {
         uint32_t v[3][16];
 #pragma unroll
         for (int g = 0; g < 3; g++) OZ_TMEM_LD16(lane_base + (uint32_t)(g * OZ2_ROWS + cc), v[g]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int c = 0; c < 16; c++) {
-          double lo = (double)(int)v[2][c];
-          lo = fma(lo, 0.00390625, (double)(int)v[1][c]);
-          lo = fma(lo, 0.00390625, (double)(int)v[0][c]);
+          double lo = oz_i2d(v[2][c]);
+          lo = fma(lo, 0.00390625, oz_i2d(v[1][c]));
+          lo = fma(lo, 0.00390625, oz_i2d(v[0][c]));
           const double acc = fma(lo, 2.3283064365386963e-10, my_park[(size_t)(cc + c) * TILE_ROWS]);
           const double w = acc * __ldg(row_scale + rb * OZ2_ROWS + cc + c);
           ssq = fma(w, w, ssq);
