@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__ Vs, int nKC,
                     const double* __restrict__ row_scale, const int* __restrict__ rb_list,
                     const int* __restrict__ rb_count, int max_rb, double* __restrict__ park,
-                    double* __restrict__ ssqp, int chunk_cands) {
+                    double* __restrict__ ssqp, int chunk_cands, int n_splits, int n_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)OZ2_STAGES * OZ2_STAGE_BYTES);
   uint64_t* empty = full + OZ2_STAGES;
@@ -231,9 +231,9 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int split = blockIdx.x, tile = blockIdx.y;
-  const int n_rb = rb_count[split];
-  const int* my_rb = rb_list + (size_t)split * max_rb;
+  // persistent: work item w = (tile, split), split fastest, so that the row splits of one
+  // candidate tile run at the same time on neighbouring SMs and share its K* digits in L2
+  const int n_items = n_splits * n_tiles;
 
   if (tid == 0) {
     for (int s = 0; s < OZ2_STAGES; s++) {
@@ -256,8 +256,12 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
 
   if (warp == 4) {
     if (lane == 0) {   // ---- producer
-      const uint8_t* Abase = Ksl + (size_t)tile * nKC * (size_t)(OZ_NS * OZ_A_BYTES);
       int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int split = w % n_splits, tile = w / n_splits;
+      const int n_rb = rb_count[split];
+      const int* my_rb = rb_list + (size_t)split * max_rb;
+      const uint8_t* Abase = Ksl + (size_t)tile * nKC * (size_t)(OZ_NS * OZ_A_BYTES);
       for (int r = 0; r < n_rb; r++) {
         const int rb = my_rb[r];
         const uint8_t* Bbase = Vs + (size_t)rb * nKC * (size_t)(OZ_NS * OZ2_B_BYTES);
@@ -275,10 +279,15 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
           }
         }
       }
+      }
     }
   } else if (warp == 5) {
     if (lane == 0) {   // ---- MMA issuer
       int it = 0, t = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int split = w % n_splits;
+      const int n_rb = rb_count[split];
+      const int* my_rb = rb_list + (size_t)split * max_rb;
       for (int r = 0; r < n_rb; r++) {
         const int nch = 4 * (my_rb[r] + 1);
         for (int pass = 0; pass < 2; pass++, t++) {
@@ -314,15 +323,20 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
           oz_commit(tmem_full);
         }
       }
+      }
     }
   } else {
     // ---- epilogue: thread = candidate (TMEM lane); 128 columns = rows of V
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     double* my_park = park + ((size_t)(smid % OZ2_PARK_SLOTS) * OZ2_ROWS) * TILE_ROWS + tid;
-    double ssq = 0.0;
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     int t = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    const int split = w % n_splits, tile = w / n_splits;
+    const int n_rb = rb_count[split];
+    const int* my_rb = rb_list + (size_t)split * max_rb;
+    double ssq = 0.0;
     for (int r = 0; r < n_rb; r++) {
       const int rb = my_rb[r];
       // pass 1: hi = S0 + S1/256 + S2/256^2 + S3/256^3 (exact), parked per (column, candidate)
@@ -369,6 +383,7 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
       oz_arrive(tmem_empty);
     }
     ssqp[(size_t)split * chunk_cands + tile * TILE_ROWS + tid] = ssq;
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -600,9 +615,9 @@ void ozaki_contract(gpry_state* st, const uint8_t* Ksl, int tiles, int chunk_can
   dim3 grid(st->oz_splits, tiles);
   const int* counts = st->oz_rb.p + (size_t)st->oz_splits * st->oz_max_rb;
   if (st->oz_rows == OZ2_ROWS)
-    oz2_contract_kernel<<<grid, OZ_THREADS, OZ2_SMEM, s>>>(
+    oz2_contract_kernel<<<std::min(st->n_sm, st->oz_splits * tiles), OZ_THREADS, OZ2_SMEM, s>>>(
         Ksl, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p, counts, st->oz_max_rb,
-        st->oz_park.p, st->ssqp.p, chunk_cands);
+        st->oz_park.p, st->ssqp.p, chunk_cands, st->oz_splits, tiles);
   else
     oz_contract_kernel<<<grid, OZ_THREADS, OZ_SMEM, s>>>(
         Ksl, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p, counts, st->oz_max_rb,
