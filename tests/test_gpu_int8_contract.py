@@ -29,11 +29,13 @@ def test_int8_matches_golden_and_fp64(dev, name):
     Xc = np.resize(g["Xc"], (max(len(g["Xc"]), 700), g["d"]))        # > 64 rows: tiled path
     n = len(g["Xc"])
     out = {}
-    for mode in ("fp64", "int8"):
+    for mode in ("fp64", "int8_1pass", "int8"):
         dev.set_contract_mode(mode)
         out[mode] = dev.predict_logexp(Xc, float(g["zeta"]), float(g["noise_level"]), st.y_max)
     dev.set_contract_mode("int8")
-    for mode in ("fp64", "int8"):
+    # the one-pass and the two-pass integer kernels form the same exact digit sums
+    assert scaled_err(out["int8"][1] ** 2, out["int8_1pass"][1] ** 2, sy ** 2) < 1e-14
+    for mode in ("fp64", "int8_1pass", "int8"):
         mean, std, acq = out[mode]
         assert scaled_err(mean[:n], g["mean"], sy) < TOL
         assert scaled_err(std[:n] ** 2, g["std"] ** 2, sy ** 2) < TOL
