@@ -45,6 +45,8 @@ SIGNATURES = {
                                       C.c_double, C.c_double]),
     "gpry_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                 C.c_void_p]),
+    "gpry_factor_append": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpry_factor_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpry_state_info": (C.c_int, [C.c_void_p, _c_int_p, _c_int_p, _c_int_p]),
     "gpry_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,

@@ -523,6 +523,14 @@ int gpry_factorize(gpry_state* st, int kind, int N, int d, const double* X_train
   });
 }
 
+int gpry_factor_append(gpry_state* st, int k, const double* X_new_t, const double* noise2_new,
+                       const double* y_t_all, const double* theta, double* out_alpha, int* info) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && X_new_t && noise2_new && y_t_all && theta && info, "NULL argument");
+    *info = factor_append_device(st, k, X_new_t, noise2_new, y_t_all, theta, out_alpha);
+  });
+}
+
 int gpry_factor_download(gpry_state* st, double* out_L, double* out_V) {
   return guarded([&] {
     GPRY_CHECK_ARG(st != nullptr, "state is NULL");

@@ -180,6 +180,8 @@ double ozaki_int8_peak_tops(gpry_state* st);
 void ozaki_prepare(gpry_state* st, cudaStream_t s);
 size_t ozaki_kslices_bytes(const gpry_state* st, int tiles);
 void ozaki_contract(gpry_state* st, const uint8_t* Ksl, int tiles, int chunk_cands, cudaStream_t s);
+int factor_append_device(gpry_state* st, int k, const double* X_new_t, const double* noise2_new,
+                         const double* y_all, const double* theta, double* out_alpha);
 void factor_download_device(gpry_state* st, double* out_L, double* out_V);
 void lml_batched_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                         const double* noise2, const double* y_t, const double* thetas, int B,

@@ -718,7 +718,7 @@ static TrainBuffers carve(gpry_state* st, int N, int d, bool need_grad, int B) {
   if (need_grad) st->f_W.reserve(NN * B);
   st->f_TT.reserve(Np * NB * B);
   st->f_Winv.reserve((size_t)b.nb * NB * NB * B);
-  const size_t nXd = al((size_t)N * d);
+  const size_t nXd = al(Np * d);   // room for rows appended later (factor_append_device)
   st->f_prob.reserve(2 * Np + nXd);
   const int nb32 = (N + 31) / 32, P = d + 1;
   size_t n = 2 * Np * B + nXd * B + al((size_t)MAX_DIM * B) + al(B) + al(2 * (size_t)B) +
@@ -935,6 +935,123 @@ void factor_download_device(gpry_state* st, double* out_L, double* out_V) {
     GPRY_CUDA(cudaMemcpyAsync(out_V, st->tmp.p, tot * 8, cudaMemcpyDeviceToHost, s));
   }
   GPRY_CUDA(cudaStreamSynchronize(s));
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Bordered append (gpr.py:996-1020 with unchanged theta / noise / preprocessing:
+// the Kriging-believer lies of gp_acquisition.py:488-491).  The factorisation kept resident by
+// factorize_device(keep) is extended by k points, one row at a time, in O(k N^2):
+//   kvec = k(x_new, X[0..m)),  l = V kvec,  lambda^2 = k(x,x) + noise2 - |l|^2,
+//   L' = [[L, 0], [l^T, lambda]],  V' = [[V, 0], [-(V^T l)^T / lambda, 1 / lambda]]
+// then alpha_ = V'^T (V' y_).  Same N_pad only (the caller refactorises when the padded size
+// changes); not positive definite -> info = failing order, the resident factor is dropped.
+// ---------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void append_krow_kernel(const double* __restrict__ T, int d, int m, double c,
+                                   double diag, double* __restrict__ krow) {
+  // krow[j] = c g(|T_m - T_j|) for j < m, krow[m] = diag
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > m) return;
+  if (j == m) {
+    krow[m] = diag;
+    return;
+  }
+  double r2 = 0.0;
+  for (int q = 0; q < d; q++) {
+    double df = T[(size_t)m * d + q] - T[(size_t)j * d + q];
+    r2 = fma(df, df, r2);
+  }
+  krow[j] = c * stationary_value<KIND>(r2);
+}
+// Lrow (= row m of K on entry) <- [l, lambda]; scal[0] = lambda, info = m + 1 if not PD
+__global__ void __launch_bounds__(256)
+append_pivot_kernel(const double* __restrict__ l, int m, double* __restrict__ Lrow,
+                    double* __restrict__ scal, int* __restrict__ info) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int j = threadIdx.x; j < m; j += 256) s = fma(l[j], l[j], s);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double lam2 = Lrow[m] - red[0];
+  __syncthreads();
+  const bool ok = lam2 > 0.0 && *info == 0;
+  const double lam = ok ? sqrt(lam2) : 1.0;
+  for (int j = threadIdx.x; j < m; j += 256) Lrow[j] = l[j];
+  if (threadIdx.x == 0) {
+    Lrow[m] = lam;
+    scal[0] = lam;
+    if (!ok && *info == 0) *info = m + 1;
+  }
+}
+// column m of VT (= row m of V'): VT[j][m] = -z[j] / lambda (j < m), VT[m][m] = 1 / lambda
+__global__ void append_vcol_kernel(const double* __restrict__ z, int m, int Np,
+                                   const double* __restrict__ scal, double* __restrict__ VT) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > m) return;
+  const double inv = 1.0 / scal[0];
+  VT[(size_t)j * Np + m] = j == m ? inv : -z[j] * inv;
+}
+
+int factor_append_device(gpry_state* st, int k, const double* X_new_t, const double* noise2_new,
+                         const double* y_all, const double* theta, double* out_alpha) {
+  if (!st->f_valid) throw GpryError{GPRY_ERR_STATE, "no device-resident factorization"};
+  GPRY_CUDA(cudaSetDevice(st->device));
+  const int N = st->f_N, d = st->f_d, kind = st->f_kind, Np = round_up(N, NB), N2 = N + k;
+  GPRY_CHECK_ARG(k >= 1 && round_up(N2, NB) == Np, "append: the padded size must not change");
+  cudaStream_t s = 0;
+  st->f_valid = false;
+  TrainBuffers b = carve(st, N, d, false, 1);       // same pointers: sizes depend on Np only
+  const double c = exp(theta[0]);
+  std::vector<double> Tn((size_t)k * d);
+  for (int i = 0; i < k; i++)
+    for (int q = 0; q < d; q++) Tn[(size_t)i * d + q] = X_new_t[(size_t)i * d + q] / exp(theta[1 + q]);
+  GPRY_CUDA(cudaMemcpyAsync(b.X + (size_t)N * d, X_new_t, (size_t)k * d * 8, cudaMemcpyHostToDevice, s));
+  GPRY_CUDA(cudaMemcpyAsync(b.T + (size_t)N * d, Tn.data(), (size_t)k * d * 8, cudaMemcpyHostToDevice, s));
+  GPRY_CUDA(cudaMemcpyAsync(b.noise2 + N, noise2_new, (size_t)k * 8, cudaMemcpyHostToDevice, s));
+  GPRY_CUDA(cudaMemcpyAsync(b.y, y_all, (size_t)N2 * 8, cudaMemcpyHostToDevice, s));
+  GPRY_CUDA(cudaMemsetAsync(b.info, 0, sizeof(int), s));
+  st->tmp.reserve(2 * (size_t)Np);
+  double* l = st->tmp.p;
+  double* z = st->tmp.p + Np;
+  for (int i = 0; i < k; i++) {
+    const int m = N + i;
+    double* Lrow = b.K + (size_t)m * Np;
+    const double diag = c + noise2_new[i];
+    const int nblk = (m + 1 + 255) / 256;
+    switch (kind) {
+      case GPRY_KERNEL_RBF:
+        append_krow_kernel<GPRY_KERNEL_RBF><<<nblk, 256, 0, s>>>(b.T, d, m, c, diag, Lrow);
+        break;
+      case GPRY_KERNEL_MATERN15:
+        append_krow_kernel<GPRY_KERNEL_MATERN15><<<nblk, 256, 0, s>>>(b.T, d, m, c, diag, Lrow);
+        break;
+      default:
+        append_krow_kernel<GPRY_KERNEL_MATERN25><<<nblk, 256, 0, s>>>(b.T, d, m, c, diag, Lrow);
+    }
+    gemv_vt_t_kernel<<<dim3(Np / 32, 1), 256, 0, s>>>(b.VT, Np, m, Lrow, l);          // l = V kvec
+    append_pivot_kernel<<<1, 256, 0, s>>>(l, m, Lrow, b.scal, b.info);
+    gemv_vt_kernel<<<dim3((Np * 32 + 255) / 256, 1), 256, 0, s>>>(b.VT, Np, m, l, z);  // z = V^T l
+    append_vcol_kernel<<<nblk, 256, 0, s>>>(z, m, Np, b.scal, b.VT);
+    GPRY_CUDA(cudaGetLastError());
+  }
+  gemv_vt_t_kernel<<<dim3(Np / 32, 1), 256, 0, s>>>(b.VT, Np, N2, b.y, b.t);
+  gemv_vt_kernel<<<dim3((Np * 32 + 255) / 256, 1), 256, 0, s>>>(b.VT, Np, N2, b.t, b.alpha);
+  GPRY_CUDA(cudaGetLastError());
+  int h_info = 0;
+  GPRY_CUDA(cudaMemcpyAsync(&h_info, b.info, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (out_alpha)
+    GPRY_CUDA(cudaMemcpyAsync(out_alpha, b.alpha, (size_t)N2 * 8, cudaMemcpyDeviceToHost, s));
+  GPRY_CUDA(cudaStreamSynchronize(s));
+  if (h_info == 0) {
+    st->f_valid = true;
+    st->f_N = N2;
+  }
+  return h_info;
 }
 
 void lml_batched_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,

@@ -319,6 +319,22 @@ class DeviceGP:
             self._f_N, self._f_d, self._f_kind = N, d, kind
         return L, V, alpha_, logdet_half.value, info.value
 
+    def factor_append(self, X_new_, noise2_new, y_all_, theta):
+        """Extend the resident factorisation by the rows of X_new_ -> (alpha_, info)."""
+        X_new_ = np.atleast_2d(as_f64(X_new_))
+        k, d = X_new_.shape
+        noise2_new = as_f64(np.broadcast_to(noise2_new, (k,)))
+        N2 = self._f_N + k
+        y_all_ = as_f64(y_all_, (N2,))
+        theta = as_f64(theta, (d + 1,))
+        alpha_ = np.empty(N2)
+        info = C.c_int(0)
+        check(self._lib.gpry_factor_append(self._h, k, ptr(X_new_), ptr(noise2_new), ptr(y_all_),
+                                           ptr(theta), ptr(alpha_), C.byref(info)))
+        if info.value == 0:
+            self._f_N = N2
+        return alpha_, info.value
+
     def factor_download(self, want_L=True, want_V=True):
         """(L_, V_) of the factorisation kept on the device by ``factorize(keep_on_device=True)``."""
         N = self._f_N

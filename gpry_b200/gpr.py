@@ -179,7 +179,8 @@ class GaussianProcessRegressor:
         self._factor_resident = False   # L_ / V_ live on the device only (see the properties)
 
     # ------------------------------------------------------------------ pickling / copies
-    _NOT_COPIED = ("_dev", "_dev_dirty", "_clf_bound", "_clf_const", "_factor_resident")
+    _NOT_COPIED = ("_dev", "_dev_dirty", "_clf_bound", "_clf_const", "_factor_resident",
+                   "_fact_sig")
 
     def __getstate__(self):
         self._materialize_factor()      # L_ / V_ may still live on the device only
@@ -581,16 +582,36 @@ class GaussianProcessRegressor:
         N = len(self.y_train_)
         if self._dev is None:
             self._dev = DeviceGP(self.device)
-        self._factor_resident = False      # whatever was resident is overwritten from here on
-        _, _, alpha_, _, info = self._dev.factorize(
-            kind, self.X_train_, np.broadcast_to(self.alpha, (N,)), self.y_train_,
-            self.kernel_.theta, want_L=False, want_V=False, keep_on_device=True)
+        noise2 = np.ascontiguousarray(np.broadcast_to(self.alpha, (N,)), dtype=float)
+        theta = np.array(self.kernel_.theta, dtype=float)
+        alpha_, info = None, 0
+        sig = self.__dict__.get("_fact_sig")
+        # Bordered append instead of a refactorisation when only rows were added at the end
+        # (same theta, same transformed old points, same noise on them): the Kriging-believer
+        # lies (gp_acquisition.py:488-491), appends with fit_classifier=False, ...
+        if (self._factor_resident and sig is not None and sig["kind"] == kind
+                and 0 < N - sig["N"] <= 64 and -(-N // 128) == -(-sig["N"] // 128)
+                and np.array_equal(sig["theta"], theta)
+                and np.array_equal(sig["X_"], self.X_train_[:sig["N"]])
+                and np.array_equal(sig["noise2"], noise2[:sig["N"]])):
+            self._factor_resident = False
+            alpha_, info = self._dev.factor_append(self.X_train_[sig["N"]:], noise2[sig["N"]:],
+                                                   self.y_train_, theta)
+            self.n_appends_without_refactor = self.__dict__.get("n_appends_without_refactor", 0) + 1
+        else:
+            self._factor_resident = False  # whatever was resident is overwritten from here on
+            _, _, alpha_, _, info = self._dev.factorize(
+                kind, self.X_train_, noise2, self.y_train_, theta, want_L=False, want_V=False,
+                keep_on_device=True)
         if info != 0:
+            self._fact_sig = None
             raise np.linalg.LinAlgError(
                 "The kernel, %s, is not returning a positive definite matrix. Try gradually "
                 "increasing the 'noise_level' parameter of your GaussianProcessRegressor "
                 "estimator." % self.kernel_,
                 f"{info}-th leading minor of the array is not positive definite")
+        self._fact_sig = {"kind": kind, "N": N, "theta": theta, "X_": np.array(self.X_train_),
+                          "noise2": noise2}
         self._L = self._V = None           # fetched from the device on first access
         self.alpha_ = alpha_
         self._factor_resident = True

@@ -232,6 +232,19 @@ int gpry_factorize(gpry_state* st, int kind, int N, int d, const double* X_train
                    double* out_L, double* out_V, double* out_alpha,
                    double* out_logdet_half, int* info, int keep_on_device);
 
+/*
+ * Extends the factorisation kept resident by gpry_factorize(..., keep_on_device = 1) by k points
+ * appended at the end of the training set, in O(k N^2) instead of O(N^3): what
+ * _update_model (gpr.py:996-1020) amounts to when theta, the noise of the old points and the
+ * pre-processors are unchanged -- the Kriging-believer lies of gp_acquisition.py:488-491.
+ * X_new_t (k x d, transformed), noise2_new (k), y_t_all (N + k, all targets), theta as given to
+ * gpry_factorize; out_alpha (N + k, may be NULL).  The padded size round_up(N, 128) must not
+ * change (GPRY_ERR_ARG otherwise: refactorise).  *info > 0: not positive definite, the resident
+ * factorisation is dropped.  Follow with gpry_state_adopt_factorization.  Host pointers.
+ */
+int gpry_factor_append(gpry_state* st, int k, const double* X_new_t, const double* noise2_new,
+                       const double* y_t_all, const double* theta, double* out_alpha, int* info);
+
 /* L and / or V (N x N row major, lower, upper triangle zeroed; either may be NULL) of the
  * factorisation kept resident by the last gpry_factorize(..., keep_on_device = 1) on this
  * state: lets the host attributes L_ / V_ (gpr.py:1456-1457) be fetched only when something

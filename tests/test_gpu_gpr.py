@@ -384,3 +384,52 @@ def test_trust_region_mask_on_device():
     assert np.all(acq_call[out] == -np.inf)
     fin = ~out & np.isfinite(a0)
     assert np.array_equal(acq_call[fin], a0[fin])
+
+
+def test_bordered_append_matches_refactorisation():
+    """with theta, the noise of the old points and the pre-processors unchanged
+    (the Kriging-believer lies, gp_acquisition.py:488-491) `_update_model` extends the resident
+    factorisation row by row; the result is the factorisation of the enlarged matrix."""
+    g = load_golden("rbf_d8_n300")
+    rng = np.random.default_rng(9)
+    lo, hi = g["bounds"][:, 0], g["bounds"][:, 1]
+    X_new = lo + (hi - lo) * rng.random((90, g["d"]))
+    gpr = make_gpr(g)
+    y_new = gpr.predict(X_new)                        # lies
+    Xc = g["Xc"]
+    n_app = 0
+    added = 0
+    for k in (1, 3, 7, 1, 40, 30, 8):                 # 300 -> 390: crosses N_pad = 384 at the 6th
+        sl = slice(added, added + k)
+        gpr.append_to_data(X_new[sl], y_new[sl], fit_gpr=False, fit_classifier=False)
+        added += k
+        crossed = -(-(300 + added) // 128) != -(-(300 + added - k) // 128)
+        if not crossed:
+            n_app += 1
+        assert gpr.__dict__.get("n_appends_without_refactor", 0) == n_app
+        # reference: a regressor that factorises the enlarged training set from scratch, with
+        # the same (frozen) pre-processors
+        full = make_gpr(g)
+        full.append_to_data(X_new[:added], y_new[:added], fit_gpr=False, fit_classifier=False)
+        full._fact_sig = None
+        full.newly_appended_for_inv = 1
+        full._update_model()                          # full factorisation of all 300 + added
+        assert full.__dict__.get("n_appends_without_refactor", 0) <= 1
+        scale = np.abs(full.alpha_).max()
+        assert np.max(np.abs(gpr.alpha_ - full.alpha_)) < 1e-9 * scale
+        m1, s1 = gpr.predict(Xc, return_std=True)
+        m2, s2 = full.predict(Xc, return_std=True)
+        sy = float(g["y_std"])
+        assert scaled_err(m1, m2, sy) < TOL and scaled_err(s1 ** 2, s2 ** 2, sy ** 2) < TOL
+    assert n_app == 6
+    # lazily fetched host factors are those of the enlarged matrix
+    N = gpr.n
+    assert gpr.L_.shape == (N, N) and gpr.V_.shape == (N, N)
+    K = gpr.L_ @ gpr.L_.T
+    Kref = gpr.kernel_(gpr.X_train_) + np.diag(np.broadcast_to(gpr.alpha, (N,)))
+    assert np.max(np.abs(K - Kref)) < 1e-10 * np.abs(Kref).max()
+    assert np.max(np.abs(gpr.V_ @ gpr.L_ - np.eye(N))) < 1e-8
+    # a change of the noise of the old points (y pre-processor refit) must not take the shortcut
+    before = gpr.n_appends_without_refactor
+    gpr.append_to_data(X_new[:1] + 1e-3, y_new[:1], fit_gpr=False)      # fit_classifier=True
+    assert gpr.n_appends_without_refactor == before
