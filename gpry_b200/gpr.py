@@ -94,7 +94,7 @@ class GaussianProcessRegressor:
                  preprocessing_X=None, preprocessing_y=None,
                  account_for_inf=None, inf_threshold="20s", keep_min_finite=None,
                  trust_region_factor=None, trust_region_nstd=None,
-                 bounds=None, random_state=None, verbose=1, device=None):
+                 bounds=None, random_state=None, verbose=1, device=None, contraction=None):
         self.n_last_appended = 0
         self.n_last_appended_finite = 0
         self.newly_appended_for_inv = 0
@@ -172,6 +172,9 @@ class GaussianProcessRegressor:
             else:
                 self._diff_threshold = float(inf_threshold)
         self.device = default_device() if device is None else int(device)
+        # variance contraction of large pools: None = library default ("int8": exact integer
+        # split on the INT8 tensor cores), "fp64" = FP64 tensor cores, "int8_1pass"
+        self.contraction = contraction
         self._dev = None          # DeviceGP holding the predict state (never pickled)
         self._dev_dirty = True
         self._clf_bound = None    # (id, version) of the classifier bound to the device state
@@ -623,6 +626,8 @@ class GaussianProcessRegressor:
         if self._dev is None:
             self._dev = DeviceGP(self.device)
             self._dev_dirty = True
+        if self.__dict__.get("contraction"):
+            self._dev.set_contract_mode(self.contraction)
         if self._dev_dirty:
             kind, c, ell = self._kernel_spec()
             px, py = self.preprocessing_X, self.preprocessing_y

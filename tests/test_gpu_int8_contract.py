@@ -124,3 +124,21 @@ def test_int8_used_only_where_supported(dev):
         dev.set_contract_mode("int8")
         b = dev.predict(Xc, return_std=True)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_regressor_contraction_switch():
+    """`GaussianProcessRegressor(contraction=...)` selects the kernel; results agree to 1e-12."""
+    from copy import deepcopy
+    from test_gpu_gpr import make_gpr
+    g = load_golden("rbf_d8_n1000")
+    sy = float(g["y_std"])
+    Xc = np.resize(g["Xc"], (800, g["d"]))
+    out = {}
+    for mode in (None, "fp64", "int8_1pass"):
+        gpr = make_gpr(g, contraction=mode)
+        out[mode] = gpr.predict(Xc, return_std=True)
+        assert deepcopy(gpr).contraction == mode
+    assert np.array_equal(out[None][0], out["fp64"][0])
+    assert scaled_err(out[None][1] ** 2, out["fp64"][1] ** 2, sy ** 2) < 1e-12
+    assert scaled_err(out[None][1] ** 2, out["int8_1pass"][1] ** 2, sy ** 2) < 1e-14
+    assert not np.array_equal(out[None][1], out["fp64"][1])      # really two different kernels
