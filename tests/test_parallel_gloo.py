@@ -1,6 +1,7 @@
 """world_size-2 tests (gloo, CPU) of the multi-process host logic: strided sharding and merge
 (mpi.py:105-131), restart split (mpi.py:80-102), survivor all-gather, best-fit selection and
-the sharded NORA ranking (result on 2 ranks == result on 1 rank)."""
+the sharded NORA ranking (result on 2 ranks == result on 1 rank), and the restart-split
+BatchOptimizer (every rank returns the same batch)."""
 import os
 import socket
 import sys
@@ -30,9 +31,11 @@ class FakeDeviceGPR:
         self.preprocessing_y = self._PY(st.y_std)
         self.n_eval = 0
 
-    def predict(self, X, return_std=False, validate=True):
+    def predict(self, X, return_std=False, validate=True, return_mean_grad=False,
+                return_std_grad=False):
         self.n_eval += len(X)
-        return orc.predict(self.st, X, return_std=return_std)
+        return orc.predict(self.st, X, return_std=return_std, return_mean_grad=return_mean_grad,
+                           return_std_grad=return_std_grad)
 
     def predict_std(self, X, validate=True):
         return orc.predict_std(self.st, X)
@@ -44,6 +47,29 @@ class FakeDeviceGPR:
 
     def _device_state(self):
         return self
+
+    # --- what BatchOptimizer / LogExp.__call__ use (oracle arithmetic, one point at a time)
+    infinities_classifier = None
+    trust_bounds = None
+
+    @property
+    def X_train(self):
+        return self.st.X_train
+
+    def predict_logexp(self, X, zeta, noise_level=None):
+        self.n_eval += len(X)
+        return orc.predict_logexp(self.st, X, zeta=zeta)
+
+    def predict_grad_batch(self, X):
+        self.n_eval += len(X)
+        rows = [orc.predict(self.st, x[None], return_std=True, return_mean_grad=True,
+                            return_std_grad=True) for x in X]
+        return (np.array([r[0][0] for r in rows]), np.array([r[1][0] for r in rows]),
+                np.array([r[2] for r in rows]), np.array([r[3] for r in rows]))
+
+    def append_to_data(self, X, y, noise_level=None, fit_gpr=False, fit_classifier=False):
+        self.st = self.st.appended(X, y)
+        self.y_max = self.st.y_max
 
     def posterior_cov(self, X):
         X_ = self.st.transform_X(X)
@@ -109,6 +135,24 @@ def _worker(rank, world, port, out_dir):
     X_pool, y_pool, acq_pool = nora.multi_add(gpr, n_points=n_points, X_mc=Xp)
     assert np.array_equal(X_pool, Xp[g["pool_idx_single_sort_acq"]])
     np.save(os.path.join(out_dir, f"pool_{rank}.npy"), X_pool)
+    # BatchOptimizer: restarts split over the ranks (mpi.split_number_for_parallel_processes,
+    # gp_acquisition.py:454-458), results gathered, every rank picks the same optimum and
+    # appends the same lie
+    from gpry_b200.gp_acquisition import BatchOptimizer
+    from gpry_b200.preprocessing import Normalize_bounds
+    opt = BatchOptimizer(g["bounds"], preprocessing_X=Normalize_bounds(g["bounds"]),
+                         acq_func=LogExp(zeta=g["zeta"]), n_restarts_optimizer=5, verbose=0)
+    gpr3 = FakeDeviceGPR(oracle_state(g))
+    n0 = len(gpr3.X_train)
+    Xb, yb, ab = opt.multi_add(gpr3, n_points=2, rng=np.random.default_rng(40 + rank))
+    assert len(gpr3.X_train) == n0                      # the caller's regressor is untouched
+    assert Xb.shape == (2, g["d"]) and np.all(np.isfinite(ab)) and gpr3.n_eval > 0
+    lo, hi = g["bounds"][:, 0], g["bounds"][:, 1]
+    assert np.all(Xb >= lo - 1e-12) and np.all(Xb <= hi + 1e-12)
+    acq = LogExp(zeta=g["zeta"])
+    assert abs(acq(Xb[:1], gpr3)[0] - ab[0]) < 1e-8 * max(1.0, abs(ab[0]))
+    assert ab[0] >= acq(gpr3.X_train[-1:], gpr3)[0] - 1e-9      # restart 0 starts there (rank 0)
+    np.save(os.path.join(out_dir, f"bopt_{rank}.npy"), np.concatenate([Xb.ravel(), yb, ab]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -119,6 +163,7 @@ def test_world_size_2(tmp_path):
     a = np.load(tmp_path / "pool_0.npy")
     b = np.load(tmp_path / "pool_1.npy")
     assert np.array_equal(a, b)      # every rank ends with the same pool (as after the bcast)
+    assert np.array_equal(np.load(tmp_path / "bopt_0.npy"), np.load(tmp_path / "bopt_1.npy"))
 
 
 def test_serial_fallbacks():
