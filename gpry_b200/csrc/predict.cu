@@ -124,15 +124,25 @@ kstar_build_kernel(const double* __restrict__ X, int64_t M, int d, int64_t cand0
         kv[jj] = kernel_value<KIND>(r2, c);
         mp = fma(kv[jj], As[j4 + jj], mp);
         if (WMODE == 2) {
-          // k*/c in [0, 1] as a 55-bit fixed-point number in OZ_NS balanced base-256 digits
-          long long t = __double2ll_rn(kv[jj] * slice_scale);
-#pragma unroll
-          for (int p = OZ_NS - 1; p >= 1; p--) {
-            const int dg = (int)(signed char)(t & 0xFF);
-            t = (t - dg) >> 8;
-            packs[p][q4] |= (uint32_t)(dg & 0xFF) << (8 * jj);
-          }
-          packs[0][q4] |= (uint32_t)((int)t & 0xFF) << (8 * jj);
+          // k*/c in [0, 1] as a 55-bit fixed-point number t = hi 2^24 + lo in OZ_NS = 7 balanced
+          // base-256 digits.  Both halves come out of the mantissa of (x + 1.5 2^52) -- no
+          // 64-bit integer arithmetic, no F2I: hi = rint(x 2^30) exactly, lo = rint of the exact
+          // remainder times 2^24.
+          const double xs = kv[jj] * slice_scale;               // slice_scale = 2^30 / c
+          const double m1 = xs + 6755399441055744.0;
+          int hi = __double2loint(m1);
+          const double rem = xs - (m1 - 6755399441055744.0);    // exact, |rem| <= 0.5
+          int lo = __double2loint(fma(rem, 16777216.0, 6755399441055744.0));
+          const uint32_t sel = 0x3210u ^ ((0x4u ^ (uint32_t)jj) << (4 * jj));   // byte jj <- digit
+          int dg;
+          dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[6][q4] = __byte_perm(packs[6][q4], dg, sel);
+          dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[5][q4] = __byte_perm(packs[5][q4], dg, sel);
+          dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[4][q4] = __byte_perm(packs[4][q4], dg, sel);
+          hi += lo;                                             // carry out of the low half
+          dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[3][q4] = __byte_perm(packs[3][q4], dg, sel);
+          dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[2][q4] = __byte_perm(packs[2][q4], dg, sel);
+          dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[1][q4] = __byte_perm(packs[1][q4], dg, sel);
+          packs[0][q4] = __byte_perm(packs[0][q4], hi, sel);
         }
       }
       if (WMODE == 1) {
@@ -689,7 +699,7 @@ static void launch_build(gpry_state* st, const double* dX, int64_t M, int64_t ca
   const int d = st->d, DP = st->DP;
   dim3 grid(tiles, JS), block(128);
   void* kout = WMODE == 2 ? (void*)st->oz_Ksl_cur : (void*)st->Ks.p;
-  const double slice_scale = 18014398509481984.0 / st->c;   // 2^54 / c
+  const double slice_scale = 1073741824.0 / st->c;           // 2^30 / c (see kstar_build, WMODE 2)
   if (d <= MAX_DIM_REG) {
     size_t smem = ((size_t)NJ * DP + NJ + 128 * d + (d & 1)) * 8 + 16;
 #define GPRY_LAUNCH_BUILD(DPV)                                                                \
