@@ -119,7 +119,7 @@ int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const doub
  *                                 to within the rounding error of an FP64 dot product.  Used for
  *                                 512 <= N_pad <= 16384, d <= 32 and more than 64 candidates per
  *                                 call; other calls use FP64.  The environment variable
- *                                 GPRY_B200_CONTRACT=fp64|int8 sets the initial mode of new states.
+ *                                 GPRY_B200_CONTRACT=fp64|int8|int8_1pass sets the initial mode of new states.
  */
 #define GPRY_CONTRACT_FP64 0
 #define GPRY_CONTRACT_INT8 1       /* two passes over the digit groups, 128 x 128 x 32 MMAs */
