@@ -233,9 +233,18 @@ def main():
     # upper clipping of the mean active (clip_factor = 1: nothing may exceed max(y_train))
     case(gpry, "rbf_d4_n150_clip1", "rbf", 150, 4, 2048, 18, 0.35, with_lml=False,
          clip_factor=1.0)
+    # higher dimensions, and sizes whose pools take the INT8 tensor-core contraction
+    # (N_pad >= 512, more than 64 candidates)
+    extra_cases(gpry)
     nonpd_case(gpry)
     fit_case(gpry)
     loop_case(gpry)
+
+
+def extra_cases(gpry):
+    case(gpry, "rbf_d16_n400", "rbf", 400, 16, 256, 19, 1.0)
+    case(gpry, "matern15_d20_n600", "matern15", 600, 20, 700, 20, 1.5, c=2.0)
+    case(gpry, "matern25_d6_n640", "matern25", 640, 6, 700, 21, 0.6, with_lml=False)
 
 
 if __name__ == "__main__":
