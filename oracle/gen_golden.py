@@ -245,6 +245,9 @@ def extra_cases(gpry):
     case(gpry, "rbf_d16_n400", "rbf", 400, 16, 256, 19, 1.0)
     case(gpry, "matern15_d20_n600", "matern15", 600, 20, 700, 20, 1.5, c=2.0)
     case(gpry, "matern25_d6_n640", "matern25", 640, 6, 700, 21, 0.6, with_lml=False)
+    # ranked pool of the reference on a model whose pool scoring takes the INT8 contraction
+    case(gpry, "rbf_d8_n700_pool", "rbf", 700, 8, 128, 22, 0.5, with_lml=False,
+         pool=(30000, 8))
 
 
 if __name__ == "__main__":

@@ -51,7 +51,10 @@ def test_predict_like_reference(golden):
     # fitted attributes are numpy arrays like the reference's
     N = g["N"]
     assert gpr.V_.shape == (N, N) and gpr.L_.shape == (N, N) and gpr.alpha_.shape == (N,)
-    assert scaled_err(gpr.alpha_, g["alpha_"], np.abs(g["alpha_"]).max()) < TOL
+    # K^-1 y is reproducible to ~eps cond(K) only (two FP64 routes on the host differ by 1.6e-10
+    # at cond(K) = 2e7, the rbf_d6_n700_pool case): SURVEY appendix B
+    assert scaled_err(gpr.alpha_, g["alpha_"], np.abs(g["alpha_"]).max()) \
+        < max(TOL, 5e-17 * float(g["condK"]))
     assert abs(gpr.y_max - float(g["y_max"])) == 0
 
 

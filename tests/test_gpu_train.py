@@ -30,8 +30,9 @@ def test_golden_factorize(dev, golden):
     assert info == 0
     N = g["N"]
     assert scaled_err(np.diag(L), g["L_diag"], 1.0) < TOL
-    assert scaled_err(alpha_, g["alpha_"], np.abs(g["alpha_"]).max()) < TOL
-    assert scaled_err(V[[0, N // 2, N - 1]], g["V_rows"], np.abs(g["V_rows"]).max()) < TOL
+    tol_c = max(TOL, 5e-17 * float(g["condK"]))     # reproducible to ~eps cond(K) only
+    assert scaled_err(alpha_, g["alpha_"], np.abs(g["alpha_"]).max()) < tol_c
+    assert scaled_err(V[[0, N // 2, N - 1]], g["V_rows"], np.abs(g["V_rows"]).max()) < tol_c
     assert abs(np.linalg.norm(V) - float(g["V_fro"])) < TOL * float(g["V_fro"])
     assert np.all(np.triu(L, 1) == 0) and np.all(np.triu(V, 1) == 0)
     assert abs(logdet_half - np.log(g["L_diag"]).sum()) < 1e-10 * max(1, abs(logdet_half))
