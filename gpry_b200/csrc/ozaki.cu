@@ -536,7 +536,7 @@ double ozaki_int8_peak_tops(gpry_state* st) {
 }
 
 bool ozaki_supported(const gpry_state* st) {
-  return st->has_V && st->d <= MAX_DIM_REG && st->Npad >= 512 && st->Npad <= 16384;
+  return st->has_V && st->Npad >= 512 && st->Npad <= 16384;
 }
 
 // digits of V and the balanced assignment of row blocks to row splits (once per upload and

@@ -43,6 +43,43 @@ __device__ __forceinline__ double kernel_value(double r2, double c) {
 }
 
 // ---------------------------------------------------------------------------------------
+// INT8 digits of one kernel value (ozaki.cu): k*/c in [0, 1] as the 55-bit fixed-point number
+// t = hi 2^24 + lo in OZ_NS = 7 balanced base-256 digits, digit p into byte jj of packs[p][q4].
+// Both halves come out of the mantissa of (x + 1.5 2^52) -- no 64-bit integer arithmetic, no
+// F2I: hi = rint(x 2^30) exactly, lo = rint of the exact remainder times 2^24.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void oz_push_digits(double kv, double slice_scale /* 2^30 / c */,
+                                               uint32_t (&packs)[OZ_NS][4], int q4, int jj) {
+  const double xs = kv * slice_scale;
+  const double m1 = xs + 6755399441055744.0;
+  int hi = __double2loint(m1);
+  const double rem = xs - (m1 - 6755399441055744.0);    // exact, |rem| <= 0.5
+  int lo = __double2loint(fma(rem, 16777216.0, 6755399441055744.0));
+  const uint32_t sel = 0x3210u ^ ((0x4u ^ (uint32_t)jj) << (4 * jj));   // byte jj <- digit
+  int dg;
+  dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[6][q4] = __byte_perm(packs[6][q4], dg, sel);
+  dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[5][q4] = __byte_perm(packs[5][q4], dg, sel);
+  dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[4][q4] = __byte_perm(packs[4][q4], dg, sel);
+  hi += lo;                                             // carry out of the low half
+  dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[3][q4] = __byte_perm(packs[3][q4], dg, sel);
+  dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[2][q4] = __byte_perm(packs[2][q4], dg, sel);
+  dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[1][q4] = __byte_perm(packs[1][q4], dg, sel);
+  packs[0][q4] = __byte_perm(packs[0][q4], hi, sel);
+}
+// [tile][k-chunk of 32][digit][k16 (2)][candidate (128)][16 B]: the shared-memory image of the
+// K-major operand of tcgen05.mma kind::i8
+__device__ __forceinline__ void oz_store_digits(void* Kout, int tile, int nKT, int k0, int tid,
+                                                const uint32_t (&packs)[OZ_NS][4]) {
+  uint8_t* base = reinterpret_cast<uint8_t*>(Kout) +
+                  ((size_t)tile * (nKT >> 1) + (k0 >> 5)) * (size_t)(OZ_NS * OZ_A_BYTES) +
+                  ((k0 >> 4) & 1) * (OZ_A_BYTES / 2) + tid * 16;
+#pragma unroll
+  for (int p = 0; p < OZ_NS; p++)
+    *reinterpret_cast<uint4*>(base + p * OZ_A_BYTES) =
+        make_uint4(packs[p][0], packs[p][1], packs[p][2], packs[p][3]);
+}
+
+// ---------------------------------------------------------------------------------------
 // kstar_build
 //   grid  = (tiles in chunk, JS)      block = 128 threads = the 128 candidates of a tile
 //   each block: NJ = Npad / JS training points (a multiple of 16)
@@ -123,27 +160,7 @@ kstar_build_kernel(const double* __restrict__ X, int64_t M, int d, int64_t cand0
         }
         kv[jj] = kernel_value<KIND>(r2, c);
         mp = fma(kv[jj], As[j4 + jj], mp);
-        if (WMODE == 2) {
-          // k*/c in [0, 1] as a 55-bit fixed-point number t = hi 2^24 + lo in OZ_NS = 7 balanced
-          // base-256 digits.  Both halves come out of the mantissa of (x + 1.5 2^52) -- no
-          // 64-bit integer arithmetic, no F2I: hi = rint(x 2^30) exactly, lo = rint of the exact
-          // remainder times 2^24.
-          const double xs = kv[jj] * slice_scale;               // slice_scale = 2^30 / c
-          const double m1 = xs + 6755399441055744.0;
-          int hi = __double2loint(m1);
-          const double rem = xs - (m1 - 6755399441055744.0);    // exact, |rem| <= 0.5
-          int lo = __double2loint(fma(rem, 16777216.0, 6755399441055744.0));
-          const uint32_t sel = 0x3210u ^ ((0x4u ^ (uint32_t)jj) << (4 * jj));   // byte jj <- digit
-          int dg;
-          dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[6][q4] = __byte_perm(packs[6][q4], dg, sel);
-          dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[5][q4] = __byte_perm(packs[5][q4], dg, sel);
-          dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[4][q4] = __byte_perm(packs[4][q4], dg, sel);
-          hi += lo;                                             // carry out of the low half
-          dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[3][q4] = __byte_perm(packs[3][q4], dg, sel);
-          dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[2][q4] = __byte_perm(packs[2][q4], dg, sel);
-          dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[1][q4] = __byte_perm(packs[1][q4], dg, sel);
-          packs[0][q4] = __byte_perm(packs[0][q4], hi, sel);
-        }
+        if (WMODE == 2) oz_push_digits(kv[jj], slice_scale, packs, q4, jj);
       }
       if (WMODE == 1) {
         // tile (j4 / 16), panel (j4 / 4) % 4, row tid
@@ -152,30 +169,19 @@ kstar_build_kernel(const double* __restrict__ X, int64_t M, int d, int64_t cand0
         reinterpret_cast<double2*>(p)[1] = make_double2(kv[2], kv[3]);
       }
     }
-    if (WMODE == 2) {
-      // [tile][k-chunk of 32][slice][k16 (2)][candidate (128)][16 B]: the shared-memory image
-      // of the K-major operand of tcgen05.mma kind::i8 (ozaki.cu)
-      const int k0 = j0 + j16;
-      uint8_t* base = reinterpret_cast<uint8_t*>(Kout) +
-                      ((size_t)tile * (nKT >> 1) + (k0 >> 5)) * (size_t)(OZ_NS * OZ_A_BYTES) +
-                      ((k0 >> 4) & 1) * (OZ_A_BYTES / 2) + tid * 16;
-#pragma unroll
-      for (int p = 0; p < OZ_NS; p++)
-        *reinterpret_cast<uint4*>(base + p * OZ_A_BYTES) =
-            make_uint4(packs[p][0], packs[p][1], packs[p][2], packs[p][3]);
-    }
+    if (WMODE == 2) oz_store_digits(Kout, tile, nKT, j0 + j16, tid, packs);
   }
   meanp[(size_t)blockIdx.y * chunk_cands + tile * TILE_ROWS + tid] = mp;
 }
 
 // generic-d variant (d > 32): candidate coordinates stay in shared memory
-template <int KIND, bool WRITE_KS>
+template <int KIND, int WMODE>
 __global__ void __launch_bounds__(128)
 kstar_build_generic_kernel(const double* __restrict__ X, int64_t M, int d, int DP, int64_t cand0,
                            const double* __restrict__ T, const double* __restrict__ alpha,
                            int NJ, int nKT, double c, const double* __restrict__ prm,
-                           double* __restrict__ Ks, double* __restrict__ meanp,
-                           int chunk_cands) {
+                           void* __restrict__ Kout, double* __restrict__ meanp,
+                           int chunk_cands, double slice_scale) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* Ts = reinterpret_cast<double*>(smem_raw);   // [NJ][DP]
   double* As = Ts + (size_t)NJ * DP;                  // [NJ]
@@ -195,24 +201,39 @@ kstar_build_generic_kernel(const double* __restrict__ X, int64_t M, int d, int D
   }
   __syncthreads();
   double mp = 0.0;
-  double* kout = Ks + ((size_t)tile * nKT + (j0 >> 4)) * TILE_DOUBLES + tid * 4;
-  for (int j4 = 0; j4 < NJ; j4 += 4) {
-    double kv[4];
-    for (int jj = 0; jj < 4; jj++) {
-      const double* tp = Ts + (size_t)(j4 + jj) * DP;
-      double r2 = 0.0;
-      for (int k = 0; k < DP; k++) {
-        double d0 = Us[k * 129 + tid] - tp[k];
-        r2 = fma(d0, d0, r2);
+  double* kout = reinterpret_cast<double*>(Kout) + ((size_t)tile * nKT + (j0 >> 4)) * TILE_DOUBLES +
+                 tid * 4;
+  for (int j16 = 0; j16 < NJ; j16 += 16) {
+    uint32_t packs[OZ_NS][4];
+    if (WMODE == 2) {
+#pragma unroll
+      for (int p = 0; p < OZ_NS; p++)
+#pragma unroll
+        for (int w = 0; w < 4; w++) packs[p][w] = 0u;
+    }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; q4++) {
+      const int j4 = j16 + q4 * 4;
+      double kv[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const double* tp = Ts + (size_t)(j4 + jj) * DP;
+        double r2 = 0.0;
+        for (int k = 0; k < DP; k++) {
+          double d0 = Us[k * 129 + tid] - tp[k];
+          r2 = fma(d0, d0, r2);
+        }
+        kv[jj] = kernel_value<KIND>(r2, c);
+        mp = fma(kv[jj], As[j4 + jj], mp);
+        if (WMODE == 2) oz_push_digits(kv[jj], slice_scale, packs, q4, jj);
       }
-      kv[jj] = kernel_value<KIND>(r2, c);
-      mp = fma(kv[jj], As[j4 + jj], mp);
+      if (WMODE == 1) {
+        double* p = kout + (size_t)(j4 >> 4) * TILE_DOUBLES + ((j4 >> 2) & 3) * (TILE_ROWS * 4);
+        reinterpret_cast<double2*>(p)[0] = make_double2(kv[0], kv[1]);
+        reinterpret_cast<double2*>(p)[1] = make_double2(kv[2], kv[3]);
+      }
     }
-    if (WRITE_KS) {
-      double* p = kout + (size_t)(j4 >> 4) * TILE_DOUBLES + ((j4 >> 2) & 3) * (TILE_ROWS * 4);
-      reinterpret_cast<double2*>(p)[0] = make_double2(kv[0], kv[1]);
-      reinterpret_cast<double2*>(p)[1] = make_double2(kv[2], kv[3]);
-    }
+    if (WMODE == 2) oz_store_digits(Kout, tile, nKT, j0 + j16, tid, packs);
   }
   meanp[(size_t)blockIdx.y * chunk_cands + tile * TILE_ROWS + tid] = mp;
 }
@@ -726,11 +747,10 @@ static void launch_build(gpry_state* st, const double* dX, int64_t M, int64_t ca
 #undef GPRY_LAUNCH_BUILD
   } else {
     size_t smem = ((size_t)NJ * DP + NJ + (size_t)DP * 129) * 8;
-    if (WMODE == 2) throw GpryError{GPRY_ERR_ARG, "internal: sliced K* needs d <= 32"};
-    auto kern = kstar_build_generic_kernel<KIND, WMODE == 1>;
+    auto kern = kstar_build_generic_kernel<KIND, WMODE>;
     GPRY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, block, smem, s>>>(dX, M, d, DP, cand0, st->T.p, st->alpha.p, NJ, st->nKT, st->c,
-                                   st->prm_dev.p, st->Ks.p, st->meanp_cur, chunk_cands);
+                                   st->prm_dev.p, kout, st->meanp_cur, chunk_cands, slice_scale);
   }
   GPRY_CUDA(cudaGetLastError());
 }

@@ -117,8 +117,8 @@ int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const doub
  *                                 digit products on the INT8 tensor cores (tcgen05.mma kind::i8,
  *                                 int32 accumulators in TMEM), recombined in FP64; same result
  *                                 to within the rounding error of an FP64 dot product.  Used for
- *                                 512 <= N_pad <= 16384, d <= 32 and more than 64 candidates per
- *                                 call; other calls use FP64.  The environment variable
+ *                                 512 <= N_pad <= 16384 and more than 64 candidates per call;
+ *                                 other calls use FP64.  The environment variable
  *                                 GPRY_B200_CONTRACT=fp64|int8|int8_1pass sets the initial mode of new states.
  */
 #define GPRY_CONTRACT_FP64 0

@@ -112,9 +112,9 @@ def test_int8_nonfinite_and_extreme_scales(dev):
 
 
 def test_int8_used_only_where_supported(dev):
-    """Small models, wide models and small batches silently take the FP64 path: same numbers
-    whatever the mode."""
-    for N, d, M in [(300, 4, 500), (600, 40, 500), (600, 4, 64)]:
+    """Small models and small batches silently take the FP64 path: same numbers whatever the
+    mode."""
+    for N, d, M in [(300, 4, 500), (600, 4, 64)]:
         X, y, theta, bounds = orc.synthetic_problem(N, d)
         st = orc.GPState("rbf", theta, X, y, bounds=bounds)
         upload_from_oracle(dev, st)
@@ -142,3 +142,22 @@ def test_regressor_contraction_switch():
     assert scaled_err(out[None][1] ** 2, out["fp64"][1] ** 2, sy ** 2) < 1e-12
     assert scaled_err(out[None][1] ** 2, out["int8_1pass"][1] ** 2, sy ** 2) < 1e-14
     assert not np.array_equal(out[None][1], out["fp64"][1])      # really two different kernels
+
+
+def test_int8_wide_models(dev):
+    """d > 32 (candidate coordinates in shared memory instead of registers) takes the INT8
+    contraction too."""
+    N, d, M = 600, 40, 900
+    X, y, theta, bounds = orc.synthetic_problem(N, d)
+    st = orc.GPState("matern25", theta, X, y, bounds=bounds)
+    upload_from_oracle(dev, st)
+    Xc = np.random.default_rng(2).uniform(size=(M, d))
+    dev.set_contract_mode("fp64")
+    m64, s64 = dev.predict(Xc, return_std=True)
+    dev.set_contract_mode("int8")
+    m8, s8 = dev.predict(Xc, return_std=True)
+    mo, so = orc.predict(st, Xc[:200], return_std=True)
+    assert np.array_equal(m8, m64) and not np.array_equal(s8, s64)
+    assert scaled_err(s8 ** 2, s64 ** 2, st.y_std ** 2) < 1e-12
+    assert scaled_err(m8[:200], mo, st.y_std) < TOL
+    assert scaled_err(s8[:200] ** 2, so ** 2, st.y_std ** 2) < TOL
