@@ -227,8 +227,7 @@ class GaussianProcessRegressor:
     # attributes: a pickle, a deep copy, a plot, a test.
     def _materialize_factor(self):
         if self.__dict__.get("_factor_resident") and self.__dict__.get("_V") is None:
-            self._L, self._V = self._dev.factor_download()
-            self._factor_resident = False
+            self._L, self._V = self._dev.factor_download()   # the device keeps its copy
 
     @property
     def L_(self):
