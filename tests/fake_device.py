@@ -217,6 +217,8 @@ def install(monkeypatch):
 
     def workspace(device=0):
         return ws.setdefault(device, FakeDeviceGP(device))
+    import gpry_b200.svm as svm_mod
+    monkeypatch.setattr(svm_mod, "DeviceGP", FakeDeviceGP)
     monkeypatch.setattr(gpr_mod, "DeviceGP", FakeDeviceGP)
     monkeypatch.setattr(gpr_mod, "workspace", workspace)
     monkeypatch.setattr(dev_mod, "workspace", workspace)

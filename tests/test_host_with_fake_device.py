@@ -153,3 +153,69 @@ def test_patched_reference_runs_and_matches_itself(monkeypatch):
     finally:
         integration.unpatch_gpry(gpry)
     assert not isinstance(cls.__dict__.get("V_"), property)
+
+
+def test_acquisition_engines_on_fake_device(monkeypatch):
+    """NORA (ranked pool of the reference reproduced) and BatchOptimizer end to end."""
+    install(monkeypatch)
+    from conftest import golden_pool_candidates
+    from gpry_b200.acquisition_functions import LogExp
+    from gpry_b200.gp_acquisition import NORA, BatchOptimizer
+    from gpry_b200.preprocessing import Normalize_bounds
+    g = load_golden("rbf_d2_n60")
+    gpr = make_gpr(g)
+    Xp = golden_pool_candidates(g)
+    nora = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=64)
+    X_pool, y_pool, acq_pool = nora.multi_add(gpr, n_points=int(g["pool_n_points"]), X_mc=Xp)
+    assert np.array_equal(X_pool, Xp[g["pool_idx_single_sort_acq"]])
+    opt = BatchOptimizer(g["bounds"], preprocessing_X=Normalize_bounds(g["bounds"]),
+                         acq_func=LogExp(zeta=g["zeta"]), n_restarts_optimizer=4, verbose=0)
+    n0 = gpr.n
+    Xb, yb, ab = opt.multi_add(gpr, n_points=3, rng=np.random.default_rng(1))
+    assert gpr.n == n0 and Xb.shape == (3, 2) and np.all(np.isfinite(ab))
+    # the working copy factorises once (a deep copy carries host factors only), further lies
+    # are appended by bordering
+    assert len(names("factor_append")) == 1
+    acq = LogExp(zeta=g["zeta"])
+    assert abs(acq(Xb[:1], gpr)[0] - ab[0]) < 1e-8 * max(1.0, abs(ab[0]))
+
+
+def test_device_classifier_plumbing(monkeypatch):
+    """account_for_inf="SVM": trained on the host (scikit-learn), evaluated by the device
+    entries (here the fake ones); the regressor binds it after every model / classifier change."""
+    install(monkeypatch)
+    from sklearn.svm import SVC
+    from gpry_b200.gpr import GaussianProcessRegressor
+    from gpry_b200.preprocessing import Normalize_bounds, Normalize_y
+    from gpry_b200.svm import SVM
+    rng = np.random.default_rng(0)
+    bounds = np.array([[-1.0, 3.0]] * 3)
+    X = bounds[:, 0] + 4.0 * rng.random((150, 3))
+    y = -0.5 * np.sum(((X - 1.0) / 0.45) ** 2, axis=1)
+    y[:5] = -np.inf
+    gpr = GaussianProcessRegressor(kernel="RBF", bounds=bounds, noise_level=1e-2,
+                                   preprocessing_X=Normalize_bounds(bounds),
+                                   preprocessing_y=Normalize_y(), account_for_inf="SVM",
+                                   inf_threshold=12.0, verbose=0, random_state=0)
+    gpr.kernel_ = deepcopy(gpr.kernel)
+    gpr.kernel_.theta = np.log([4.0, 0.35, 0.35, 0.35])
+    gpr.append_to_data(X, y, fit_gpr=False)
+    clf = gpr.infinities_classifier
+    assert isinstance(clf, SVM) and 0 < clf.y_finite.sum() < len(y) and gpr.n == clf.y_finite.sum()
+    Xc = bounds[:, 0] + 4.0 * rng.random((4000, 3))
+    ref = SVC(C=1e7, kernel="rbf", gamma="scale").fit(clf.X_train, clf.y_finite)
+    dec_ref = ref.decision_function(gpr.preprocessing_X.transform(Xc))
+    clear = np.abs(dec_ref) > 1e-7
+    m, s = gpr.predict(Xc, return_std=True)
+    bad = (dec_ref <= 0) & clear
+    assert bad.any() and np.all(m[bad] == -np.inf) and np.all(s[bad] == 0)
+    assert np.all(np.isfinite(m[(dec_ref > 0) & clear]))
+    assert np.array_equal(clf.predict(gpr.preprocessing_X.transform(Xc))[clear], (dec_ref > 0)[clear])
+    assert np.all(gpr.predict_std(Xc)[bad] == 0)
+    assert np.all(gpr.predict_logexp(Xc, 0.5)[2][bad] == -np.inf)
+    # classifier-only refit (only infinite points appended) re-binds it on the device state
+    v0 = clf.version
+    gpr.append_to_data(bounds[:, 1][None] - 1e-3, np.array([-np.inf]), fit_gpr=False)
+    assert clf.version > v0 and gpr._clf_bound == (id(clf), v0)      # stale until the next call
+    assert gpr.predict(bounds[:, 1][None] - 1e-3)[0] == -np.inf
+    assert gpr._clf_bound == (id(clf), clf.version)
