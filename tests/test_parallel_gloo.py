@@ -1,7 +1,8 @@
 """world_size-2 tests (gloo, CPU) of the multi-process host logic: strided sharding and merge
 (mpi.py:105-131), restart split (mpi.py:80-102), survivor all-gather, best-fit selection and
 the sharded NORA ranking (result on 2 ranks == result on 1 rank), and the restart-split
-BatchOptimizer (every rank returns the same batch)."""
+BatchOptimizer (every rank returns the same batch), and the restart-parallel hyper-parameter
+fit with the real regressor class on an oracle-backed stand-in for the device."""
 import os
 import socket
 import sys
@@ -153,6 +154,30 @@ def _worker(rank, world, port, out_dir):
     assert abs(acq(Xb[:1], gpr3)[0] - ab[0]) < 1e-8 * max(1.0, abs(ab[0]))
     assert ab[0] >= acq(gpr3.X_train[-1:], gpr3)[0] - 1e-9      # restart 0 starts there (rank 0)
     np.save(os.path.join(out_dir, f"bopt_{rank}.npy"), np.concatenate([Xb.ravel(), yb, ab]))
+    # restart-parallel hyper-parameter fit (Runner._fit_gpr_parallel, run.py:1238-1301) with the
+    # real regressor class on an oracle-backed stand-in for the device: restarts split over
+    # the ranks, (lml, theta) all-gathered, every rank ends with the winner's model
+    import gpry_b200.device as dev_mod
+    import gpry_b200.gpr as gpr_mod
+    from fake_device import FakeDeviceGP
+    ws = {}
+    gpr_mod.DeviceGP = FakeDeviceGP
+    gpr_mod.workspace = dev_mod.workspace = lambda device=0: ws.setdefault(device, FakeDeviceGP(device))
+    from gpry_b200.preprocessing import Normalize_y
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fit_rbf_d2_n40.npz"))
+    fit = gpr_mod.GaussianProcessRegressor(
+        kernel="RBF", bounds=z["bounds"], noise_level=1e-2, n_restarts_optimizer=4,
+        preprocessing_X=Normalize_bounds(z["bounds"]), preprocessing_y=Normalize_y(),
+        account_for_inf=None, random_state=100 + rank, verbose=0)
+    best_rank = parallel.fit_gpr_parallel(fit, z["X_train"], z["y_train"])
+    thetas = parallel.allgather(np.array(fit.kernel_.theta))
+    assert all(np.array_equal(t, thetas[0]) for t in thetas) and 0 <= best_rank < world
+    lmls = parallel.allgather(float(fit.log_marginal_likelihood_value_))
+    assert lmls[0] == lmls[1] and np.isfinite(lmls[0]) and fit.fitted
+    preds = parallel.allgather(fit.predict(z["Xc"]))
+    assert np.array_equal(preds[0], preds[1])
+    # the reference's own fit of this case (golden): the parallel fit is at least as good
+    assert lmls[0] >= float(z["lml_opt"]) - 1e-6 * abs(float(z["lml_opt"]))
     dist.barrier()
     dist.destroy_process_group()
 
