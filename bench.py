@@ -584,6 +584,10 @@ def run_ours(args):
                        "candidates_per_gpu": M, "candidates_total": world * M, "n_train": N,
                        "dim": d, "kprime": Kp, "parallelism": f"candidate-sharded x{world}",
                        "contraction": args.contract,
+                       "contraction_arithmetic": (
+                           "f64 operands split exactly into 7 int8 digits each; int8 x int8 -> "
+                           "int32 on the tensor cores (exact), recombined and squared in f64"
+                           if args.contract == "int8" else "f64 tensor cores (DMMA)"),
                        "l2": "inputs (1.2 GB/GPU) and K* scratch (>500 MB) exceed the 126 MB L2",
                        "state_bcast_ms": t_bcast_ms},
             "e2e": e2e, "gpu_launches": int(tm["launches"]), "roofline": roofline,
