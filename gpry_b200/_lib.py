@@ -58,6 +58,7 @@ SIGNATURES = {
                                            C.c_double, C.c_double, C.c_int, C.c_int64, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, _c_int64_p, C.c_void_p]),
+    "gpry_set_excluded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "gpry_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
                             C.c_void_p, _c_int64_p, C.c_void_p]),
     "gpry_mean_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

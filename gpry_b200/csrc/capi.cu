@@ -76,20 +76,40 @@ static const double* stage_in(gpry_state* st, const double* X, size_t n, bool on
 // Host candidates: enqueue the H2D copy in blocks on a dedicated copy stream and run the
 // pipeline block by block behind the matching event, so that only the first block's copy is
 // exposed.  Device candidates: one call.
+static void run_block(gpry_state* st, const double* dXb, int64_t off, int64_t n, bool want_var,
+                      bool want_acq, double zeta, double sigma_n, double y_max, double* dm,
+                      double* ds, double* da, int64_t idx_offset, cudaStream_t s) {
+  if (st->sel.on) {     // selection: masks are applied inside finish_select (predict.cu)
+    st->sel.gbase = idx_offset + off;
+    st->sel.lbase = off;
+    st->sel.clf_dec = nullptr;
+    if (st->clf_on) {
+      st->clf_dec.reserve((size_t)n);
+      predict_pipeline(st->clf, dXb, n, true, false, false, 0, 0, 0, st->clf_dec.p, nullptr,
+                       nullptr, s);
+      st->sel.clf_dec = st->clf_dec.p;
+    }
+  }
+  predict_pipeline(st, dXb, n, dm != nullptr, want_var, want_acq, zeta, sigma_n, y_max,
+                   dm ? dm + off : nullptr, ds ? ds + off : nullptr, da ? da + off : nullptr, s);
+}
+
 static void run_pipeline_blocks(gpry_state* st, const double* X, int64_t M, bool x_dev,
                                 bool want_var, bool want_acq, double zeta, double sigma_n,
                                 double y_max, double* dm, double* ds, double* da,
-                                const double** dX_out, cudaStream_t s) {
+                                const double** dX_out, cudaStream_t s, int64_t idx_offset = 0) {
   const int d = st->d;
+  const int64_t block = (int64_t)56 * 2 * st->n_sm * TILE_ROWS;   // multiple of the chunk size
   if (x_dev) {
     *dX_out = X;
-    predict_pipeline(st, X, M, dm != nullptr, want_var, want_acq, zeta, sigma_n, y_max, dm, ds, da,
-                     s);
+    // (selection: block by block as well, so that the classifier scratch stays block sized)
+    for (int64_t off = 0; off < M; off += block)
+      run_block(st, X + off * d, off, std::min(block, M - off), want_var, want_acq, zeta, sigma_n,
+                y_max, dm, ds, da, idx_offset, s);
     return;
   }
   st->Xdev.reserve((size_t)M * d);
   *dX_out = st->Xdev.p;
-  const int64_t block = (int64_t)56 * 2 * st->n_sm * TILE_ROWS;   // multiple of the chunk size
   const int nblocks = (int)((M + block - 1) / block);
   if (nblocks <= 1) {
     TimedScope ts(st, s, T_H2D, 0);
@@ -117,9 +137,8 @@ static void run_pipeline_blocks(gpry_state* st, const double* X, int64_t M, bool
   for (int b = 0; b < nblocks; b++) {
     const int64_t off = b * block, n = std::min(block, M - off);
     if (nblocks > 1) GPRY_CUDA(cudaStreamWaitEvent(s, st->copy_events[b], 0));
-    predict_pipeline(st, st->Xdev.p + off * d, n, dm != nullptr, want_var, want_acq, zeta, sigma_n,
-                     y_max, dm ? dm + off : nullptr, ds ? ds + off : nullptr,
-                     da ? da + off : nullptr, s);
+    run_block(st, st->Xdev.p + off * d, off, n, want_var, want_acq, zeta, sigma_n, y_max, dm, ds,
+              da, idx_offset, s);
   }
 }
 
@@ -180,6 +199,8 @@ int gpry_state_destroy(gpry_state* st) {
     st->tmp.release(); st->small.release(); st->Vrm.release(); st->trust.release();
     st->pc_U.release(); st->pc_Ks.release(); st->pc_UT.release(); st->pc_G.release();
     st->VTrm.release(); st->gr_out.release(); st->clf_dec.release();
+    for (int b = 0; b < 2; b++) { st->sel_acq[b].release(); st->sel_mean[b].release(); st->sel_std[b].release(); st->sel_idx[b].release(); st->tk_pos[b].release(); }
+    st->sel_ctl.release(); st->excl.release();
     st->oz_Ksl.release(); st->oz_Vs.release(); st->oz_scale.release(); st->oz_rb.release(); st->oz_park.release();
     if (st->clf) gpry_state_destroy(st->clf);
     st->f_K.release(); st->f_VT.release(); st->f_W.release(); st->f_TT.release();
@@ -382,6 +403,19 @@ int gpry_predict_logexp(gpry_state* st, const double* X, int64_t M, double zeta,
   });
 }
 
+int gpry_set_excluded(gpry_state* st, const int64_t* rows, int n) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    GPRY_CHECK_ARG(n >= 0 && (n == 0 || rows != nullptr), "bad skip list");
+    for (int i = 1; i < n; i++) GPRY_CHECK_ARG(rows[i - 1] < rows[i], "skip list must be sorted");
+    st->n_excl = n;
+    if (n == 0) return;
+    GPRY_CUDA(cudaSetDevice(st->device));
+    st->excl.reserve((size_t)n);
+    GPRY_CUDA(cudaMemcpy(st->excl.p, rows, (size_t)n * 8, cudaMemcpyHostToDevice));
+  });
+}
+
 int gpry_predict_logexp_topk(gpry_state* st, const double* X, int64_t M, double zeta,
                              double sigma_n, double y_max, int Kp, int64_t idx_offset, int where,
                              double* out_acq, int64_t* out_idx, double* out_mean,
@@ -396,33 +430,33 @@ int gpry_predict_logexp_topk(gpry_state* st, const double* X, int64_t M, double 
     GPRY_CUDA(cudaSetDevice(st->device));
     const bool x_dev = where & GPRY_X_ON_DEVICE, o_dev = where & GPRY_OUT_ON_DEVICE;
     const int d = st->d;
-    st->o_mean.reserve(M);
-    st->o_std.reserve(M);
-    st->o_acq.reserve(M);
-    const double* dX = nullptr;
-    run_pipeline_blocks(st, X, M, x_dev, true, true, zeta, sigma_n, y_max, st->o_mean.p,
-                        st->o_std.p, st->o_acq.p, &dX, s);
-    apply_classifier(st, dX, M, st->o_mean.p, st->o_std.p, st->o_acq.p, s);
-    apply_trust_region(st, dX, M, st->o_mean.p, st->o_acq.p, s);
-    double* d_keys;
-    int64_t* d_idx;
-    int64_t n = topk_device(st, st->o_acq.p, M, Kp, idx_offset, &d_keys, &d_idx, s);
-    // gather mean/std/X of the survivors into a small device record
-    st->small.reserve((size_t)Kp * (2 + d) + 2 * MAX_DIM);
-    double* g_mean = o_dev && out_mean ? out_mean : st->small.p;
-    double* g_std = o_dev && out_std ? out_std : st->small.p + Kp;
-    double* g_X = o_dev && out_X ? out_X : st->small.p + 2 * (size_t)Kp;
-    gather_topk(st, d_idx, n, idx_offset, dX, d, st->o_mean.p, st->o_std.p,
-                out_mean ? g_mean : nullptr, out_std ? g_std : nullptr, out_X ? g_X : nullptr, s);
     const cudaMemcpyKind kind = o_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const double* dX = nullptr;
+    // Streaming selection: every chunk's finish kernel appends only the records that can
+    // still be among the Kp best (topk.cu); mean / std / acq [M] never exist.
+    const int64_t tiles = (M + TILE_ROWS - 1) / TILE_ROWS;
+    const int chunk_cands = (int)std::min<int64_t>(tiles, 2 * st->n_sm) * TILE_ROWS;
+    select_begin(st, Kp, chunk_cands, s);
+    try {
+      run_pipeline_blocks(st, X, M, x_dev, true, true, zeta, sigma_n, y_max, nullptr, nullptr,
+                          nullptr, &dX, s, idx_offset);
+    } catch (...) {
+      st->sel.on = false;
+      throw;
+    }
+    const int64_t n = select_finish(st, s);          // synchronises: n is data dependent
+    const int b = st->sel.cur;
     {
       TimedScope ts(st, s, T_D2H, 0);
-      if (out_acq) GPRY_CUDA(cudaMemcpyAsync(out_acq, d_keys, n * 8, kind, s));
-      if (out_idx) GPRY_CUDA(cudaMemcpyAsync(out_idx, d_idx, n * 8, kind, s));
-      if (!o_dev) {
-        if (out_mean) GPRY_CUDA(cudaMemcpyAsync(out_mean, g_mean, n * 8, kind, s));
-        if (out_std) GPRY_CUDA(cudaMemcpyAsync(out_std, g_std, n * 8, kind, s));
-        if (out_X) GPRY_CUDA(cudaMemcpyAsync(out_X, g_X, n * d * 8, kind, s));
+      if (out_acq) GPRY_CUDA(cudaMemcpyAsync(out_acq, st->sel_acq[b].p, n * 8, kind, s));
+      if (out_idx) GPRY_CUDA(cudaMemcpyAsync(out_idx, st->sel_idx[b].p, n * 8, kind, s));
+      if (out_mean) GPRY_CUDA(cudaMemcpyAsync(out_mean, st->sel_mean[b].p, n * 8, kind, s));
+      if (out_std) GPRY_CUDA(cudaMemcpyAsync(out_std, st->sel_std[b].p, n * 8, kind, s));
+      if (out_X) {
+        st->small.reserve((size_t)Kp * d + 2 * MAX_DIM);
+        double* g_X = o_dev ? out_X : st->small.p;
+        gather_rows(st, st->sel_idx[b].p, n, idx_offset, dX, d, g_X, s);
+        if (!o_dev) GPRY_CUDA(cudaMemcpyAsync(out_X, g_X, n * d * 8, kind, s));
       }
     }
     *n_out = n;

@@ -255,26 +255,38 @@ struct FinishParams {
   double* o_acq;
 };
 
-__device__ __forceinline__ void finish_one(const FinishParams& f, int i, bool have_var,
-                                           double ssq) {
+// mean, std and acquisition of candidate i of the chunk (in registers)
+__device__ __forceinline__ void finish_values(const FinishParams& f, int i, bool have_var,
+                                              double ssq, double& mean, double& sd, double& acq) {
   double m_ = 0.0;
   for (int s = 0; s < f.JS; s++) m_ += f.meanp[(size_t)s * f.chunk_cands + i];
-  double mean = m_ * f.y_std + f.y_mean;          // preprocessing.py:620
+  mean = m_ * f.y_std + f.y_mean;                 // preprocessing.py:620
   mean = fmin(mean, f.clip_hi);                   // gpr.py:1187-1195 (np.clip upper)
   if (isnan(m_)) mean = m_;
-  if (f.o_mean) f.o_mean[i] = mean;
+  sd = 0.0;
+  acq = 0.0;
   if (have_var) {
     if (isnan(m_)) ssq = m_;                      // a NaN in k* reaches every output (INT8 digits
                                                   // of a NaN are meaningless, the FP64 sum is not)
     double var = f.c - ssq;                       // gpr.py:1207-1208
     if (var < 0.0) var = 0.0;                     // :1214-1219
-    double sd = sqrt(var) * f.y_std;              // :1220, preprocessing.py:630
-    if (f.o_std) f.o_std[i] = sd;
-    if (f.want_acq && f.o_acq) {
+    sd = sqrt(var) * f.y_std;                     // :1220, preprocessing.py:630
+    if (f.want_acq) {
       double v = sd * sd - f.sigma_n2;            // std**2 - noise_level**2
       v = v > 0.0 ? v : 0.0;                      // np.clip(., 0, None)
-      f.o_acq[i] = f.two_zeta * (mean - f.y_max) + log(sqrt(v));
+      acq = f.two_zeta * (mean - f.y_max) + log(sqrt(v));
     }
+  }
+}
+
+__device__ __forceinline__ void finish_one(const FinishParams& f, int i, bool have_var,
+                                           double ssq) {
+  double mean, sd, acq;
+  finish_values(f, i, have_var, ssq, mean, sd, acq);
+  if (f.o_mean) f.o_mean[i] = mean;
+  if (have_var) {
+    if (f.o_std) f.o_std[i] = sd;
+    if (f.want_acq && f.o_acq) f.o_acq[i] = acq;
   }
 }
 
@@ -518,6 +530,94 @@ __global__ void finish_kernel(FinishParams f, const double* __restrict__ ssqp, i
   if (ssqp)
     for (int s = 0; s < row_splits; s++) ssq += ssqp[(size_t)s * f.chunk_cands + i];
   finish_one(f, i, ssqp != nullptr, ssq);
+}
+
+// ---------------------------------------------------------------------------------------
+// finish + selection (gpry_predict_logexp_topk): the finishing arithmetic above, the two device
+// masks (classifier: gpr.py:1145, 1172; trust region: :1201; either makes LogExp -inf,
+// acquisition_functions.py:983-992), the skip list of already proposed rows
+// (gp_acquisition.py:1037-1047), and a threshold filter against the K'-th best acquisition
+// value seen so far: warp ballot + one atomic per warp reserve the slots, only the records that
+// can still be ranked are written (see topk.cu).
+// ---------------------------------------------------------------------------------------
+struct SelectArgs {
+  double* acq;
+  int64_t* idx;
+  double* mean;
+  double* sd;
+  unsigned long long* ctl;   // [0] count, [1] threshold key, [2] overflow
+  int cap;
+  int64_t gbase;             // global index of candidate 0 of this chunk
+  int64_t lbase;             // row number in the pool of candidate 0 of this chunk
+  const int64_t* excl;       // sorted row numbers to skip
+  int n_excl;
+  const double* X;           // candidate rows of this chunk (trust region) or NULL
+  int d;
+  const double* trust_lohi;
+  double mask_value;
+  const double* clf_dec;     // classifier decisions of this chunk's rows or NULL
+};
+
+__device__ __forceinline__ unsigned long long select_key(double x) {
+  if (x != x) return 0ull;   // NaN ranks below everything (as topk.cu sortable_key)
+  unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(256)
+finish_select_kernel(FinishParams f, const double* __restrict__ ssqp, int row_splits,
+                     SelectArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool pass = false;
+  double mean = 0.0, sd = 0.0, acq = 0.0;
+  if (i < f.n_valid) {
+    double ssq = 0.0;
+    for (int s = 0; s < row_splits; s++) ssq += ssqp[(size_t)s * f.chunk_cands + i];
+    finish_values(f, i, true, ssq, mean, sd, acq);
+    if (a.clf_dec && !(a.clf_dec[i] > 0.0)) {
+      mean = a.mask_value;
+      sd = 0.0;
+      acq = -INFINITY;
+    }
+    if (a.X) {
+      bool inside = true;
+      for (int k = 0; k < a.d; k++) {
+        const double x = a.X[(size_t)i * a.d + k];
+        inside = inside && (x >= a.trust_lohi[k]) && (x <= a.trust_lohi[MAX_DIM + k]);
+      }
+      if (!inside) {
+        mean = a.mask_value;
+        acq = -INFINITY;
+      }
+    }
+    pass = select_key(acq) >= a.ctl[1];
+    if (pass && a.n_excl > 0) {      // binary search of the row number in the skip list
+      const int64_t row = a.lbase + i;
+      int lo = 0, hi = a.n_excl;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a.excl[mid] < row) lo = mid + 1; else hi = mid;
+      }
+      if (lo < a.n_excl && a.excl[lo] == row) pass = false;
+    }
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+  if (ballot == 0u) return;
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(a.ctl, (unsigned long long)__popc(ballot));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (pass) {
+    const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+    if (slot < (unsigned long long)a.cap) {
+      a.acq[slot] = acq;
+      a.idx[slot] = a.gbase + i;
+      a.mean[slot] = mean;
+      a.sd[slot] = sd;
+    } else {
+      a.ctl[2] = 1ull;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -982,7 +1082,7 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
   if (want_var && !st->has_V)
     throw GpryError{GPRY_ERR_STATE, "this state was uploaded without V: mean only"};
   GPRY_CUDA(cudaSetDevice(st->device));
-  if (M <= SMALL_M_MAX) {   // latency path, SMALL_M candidates per pass over V
+  if (M <= SMALL_M_MAX && !st->sel.on) {   // latency path, SMALL_M candidates per pass over V
     for (int m0 = 0; m0 < (int)M; m0 += SMALL_M)
       predict_small(st, dX + (size_t)m0 * st->d, std::min(SMALL_M, (int)M - m0), want_var, want_acq,
                     zeta, sigma_n, y_max, d_mean ? d_mean + m0 : nullptr,
@@ -1044,7 +1144,8 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
     fin.o_mean = d_mean ? d_mean + cand0 : nullptr;
     fin.o_std = d_std ? d_std + cand0 : nullptr;
     fin.o_acq = d_acq ? d_acq + cand0 : nullptr;
-    const bool fused = want_var && row_splits == 1 && !ozaki;
+    const bool selecting = st->sel.on;
+    const bool fused = want_var && row_splits == 1 && !ozaki && !selecting;
     if (ozaki) {
       TimedScope ts(st, s, T_CONTRACT);
       st->n_contract_launches += 1;
@@ -1058,7 +1159,24 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
           fused ? 1 : 0, fin);
       GPRY_CUDA(cudaGetLastError());
     }
-    if (!fused) {
+    if (selecting) {
+      SelectRun& r = st->sel;
+      SelectArgs a;
+      a.acq = st->sel_acq[r.cur].p; a.idx = st->sel_idx[r.cur].p;
+      a.mean = st->sel_mean[r.cur].p; a.sd = st->sel_std[r.cur].p;
+      a.ctl = st->sel_ctl.p; a.cap = r.cap;
+      a.gbase = r.gbase + cand0; a.lbase = r.lbase + cand0;
+      a.excl = st->excl.p; a.n_excl = st->n_excl;
+      a.X = st->trust_on ? dX + (size_t)cand0 * st->d : nullptr;
+      a.d = st->d; a.trust_lohi = st->trust.p; a.mask_value = st->trust_value;
+      a.clf_dec = r.clf_dec ? r.clf_dec + cand0 : nullptr;
+      {
+        TimedScope ts(st, s, T_FINISH);
+        finish_select_kernel<<<(n + 255) / 256, 256, 0, s>>>(fin, st->ssqp.p, row_splits, a);
+        GPRY_CUDA(cudaGetLastError());
+      }
+      if (++r.pending >= r.max_pending) select_compact(st, s);
+    } else if (!fused) {
       TimedScope ts(st, s, T_FINISH);
       finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(fin, want_var ? st->ssqp.p : nullptr,
                                                     row_splits);

@@ -55,6 +55,18 @@ struct EventPair {
   cudaEvent_t e0, e1;
 };
 
+// Host-side bookkeeping of one gpry_predict_logexp_topk call (the selection runs chunk by chunk
+// inside predict_pipeline; see topk.cu)
+struct SelectRun {
+  bool on = false;
+  int Kp = 0, cap = 0, cur = 0;
+  int pending = 0;            // chunks appended since the last compaction
+  int max_pending = 0;        // compaction period (the buffer holds K' + that many chunks)
+  int64_t gbase = 0;          // global index (idx_offset included) of row 0 of the current block
+  int64_t lbase = 0;          // row number in the pool of row 0 of the current block
+  const double* clf_dec = nullptr;   // classifier decisions of the current block, or NULL
+};
+
 }  // namespace gpry
 
 struct gpry_state {
@@ -106,6 +118,17 @@ struct gpry_state {
   gpry::DevBuf<double> o_mean, o_std, o_acq;   // per-candidate outputs (device)
   gpry::DevBuf<double> tk_keys[2];
   gpry::DevBuf<int64_t> tk_idx[2];
+  gpry::DevBuf<int> tk_pos[2];
+  // streaming selection of gpry_predict_logexp_topk (topk.cu): the records (acq, global index,
+  // mean, std) of the candidates that can still be among the K' best; two buffers (compaction
+  // copies the sorted K' best of one to the front of the other); sel_ctl = [count, threshold
+  // key, overflow flag]
+  gpry::DevBuf<double> sel_acq[2], sel_mean[2], sel_std[2];
+  gpry::DevBuf<int64_t> sel_idx[2];
+  gpry::DevBuf<unsigned long long> sel_ctl;
+  gpry::SelectRun sel;                   // host side of the selection in flight
+  gpry::DevBuf<int64_t> excl;            // sorted local row numbers skipped by the ranking
+  int n_excl = 0;
   gpry::DevBuf<double> tmp;              // upload staging (raw V etc.)
   gpry::DevBuf<double> small;            // small outputs (gradient, top-k records)
 
@@ -163,6 +186,11 @@ void kernel_cross_device(gpry_state* st, int kind, int d, const double* theta, c
 void kernel_gradx_device(gpry_state* st, const double* x_host, double* out_host);
 void std_grad_device(gpry_state* st, const double* x_host, double* out_grad, double* out_std);
 // topk.cu
+void select_begin(gpry_state* st, int Kp, int chunk_cands, cudaStream_t s);
+void select_compact(gpry_state* st, cudaStream_t s);
+int64_t select_finish(gpry_state* st, cudaStream_t s);
+void gather_rows(gpry_state* st, const int64_t* d_idx, int64_t n, int64_t idx_base,
+                 const double* dX, int d, double* o_X, cudaStream_t s);
 int64_t topk_device(gpry_state* st, const double* d_scores, int64_t M, int Kp, int64_t idx_base,
                     double** d_keys_out, int64_t** d_idx_out, cudaStream_t s);
 void gather_topk(gpry_state* st, const int64_t* d_idx, int64_t n, int64_t idx_base,

@@ -6,6 +6,8 @@
 // passes repeat on the survivors until one block remains.
 #include "state.cuh"
 
+#include <algorithm>
+
 namespace gpry {
 
 constexpr int TK_E = 4096;        // elements per block
@@ -106,6 +108,195 @@ int64_t topk_device(gpry_state* st, const double* d_scores, int64_t M, int Kp, i
   *d_keys_out = st->tk_keys[cur].p;
   *d_idx_out = st->tk_idx[cur].p;
   return std::min<int64_t>(Kp, M);
+}
+
+// ---------------------------------------------------------------------------------------
+// Streaming selection (gpry_predict_logexp_topk).  finish_select_kernel (predict.cu) appends
+// the record (acq, global index, mean, std) of every candidate whose key is >= the current
+// threshold tau to the record buffer with warp-aggregated atomics; tau = key of the K'-th best
+// record seen so far (0 = everything passes until K' records exist).  A compaction sorts the
+// buffer exactly (block bitonic sorts of 4096 (key, index, position) triples, repeated on the
+// per-block survivors), moves the K' best -- in output order -- to the front of the other
+// buffer and raises tau.  The per-candidate arrays mean/std/acq[M] are never written.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TK_THREADS)
+topk_rec_kernel(const double* __restrict__ keys_in, const int64_t* __restrict__ gidx_in,
+                const int* __restrict__ pos_in, const unsigned long long* __restrict__ count_ptr,
+                int64_t n, int Kp, double* __restrict__ keys_out, int64_t* __restrict__ gidx_out,
+                int* __restrict__ pos_out) {
+  extern __shared__ __align__(16) unsigned char tk_smem[];
+  uint64_t* sk = reinterpret_cast<uint64_t*>(tk_smem);
+  int64_t* si = reinterpret_cast<int64_t*>(tk_smem + TK_E * 8);
+  int* sp = reinterpret_cast<int*>(tk_smem + TK_E * 16);
+  const int tid = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * TK_E;
+  if (count_ptr) n = min(n, (int64_t)*count_ptr);
+  const double nan_value = __longlong_as_double(0x7ff8000000000000ll);
+  if (base >= n) {        // nothing in this block's range: empties
+    for (int e = tid; e < Kp; e += TK_THREADS) {
+      keys_out[(int64_t)blockIdx.x * Kp + e] = nan_value;
+      gidx_out[(int64_t)blockIdx.x * Kp + e] = INT64_MAX;
+      pos_out[(int64_t)blockIdx.x * Kp + e] = -1;
+    }
+    return;
+  }
+  for (int e = tid; e < TK_E; e += TK_THREADS) {
+    int64_t g = base + e;
+    if (g < n && gidx_in[g] != INT64_MAX) {
+      sk[e] = sortable_key(keys_in[g]);
+      si[e] = gidx_in[g];
+      sp[e] = pos_in ? pos_in[g] : (int)g;
+    } else {
+      sk[e] = 0ull;
+      si[e] = INT64_MAX;
+      sp[e] = -1;
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= TK_E; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int e = tid; e < TK_E / 2; e += TK_THREADS) {
+        int lo = 2 * e - (e & (stride - 1));
+        int hi = lo + stride;
+        bool up = ((lo & size) == 0);
+        uint64_t ka = sk[lo], kb = sk[hi];
+        int64_t ia = si[lo], ib = si[hi];
+        bool swap = up ? before(kb, ib, ka, ia) : before(ka, ia, kb, ib);
+        if (swap) {
+          int pa = sp[lo], pb = sp[hi];
+          sk[lo] = kb; si[lo] = ib; sp[lo] = pb;
+          sk[hi] = ka; si[hi] = ia; sp[hi] = pa;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int e = tid; e < Kp; e += TK_THREADS) {
+    keys_out[(int64_t)blockIdx.x * Kp + e] = key_to_double(sk[e], nan_value);
+    gidx_out[(int64_t)blockIdx.x * Kp + e] = si[e];
+    pos_out[(int64_t)blockIdx.x * Kp + e] = sp[e];
+  }
+}
+
+// the K' best (sorted) -> front of the other record buffer; count = min(count, K'); tau
+__global__ void __launch_bounds__(1024)
+select_gather_kernel(const double* __restrict__ keys, const int64_t* __restrict__ gidx,
+                     const int* __restrict__ pos, int Kp, const double* __restrict__ a_in,
+                     const double* __restrict__ m_in, const double* __restrict__ s_in,
+                     double* __restrict__ a_out, int64_t* __restrict__ i_out,
+                     double* __restrict__ m_out, double* __restrict__ s_out,
+                     unsigned long long* __restrict__ ctl) {
+  const unsigned long long count = ctl[0];
+  for (int e = threadIdx.x; e < Kp; e += blockDim.x) {
+    const int p = pos[e];
+    if (p >= 0) {
+      a_out[e] = a_in[p];
+      m_out[e] = m_in[p];
+      s_out[e] = s_in[p];
+      i_out[e] = gidx[e];
+    } else {
+      i_out[e] = INT64_MAX;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long kept = count < (unsigned long long)Kp ? count : (unsigned long long)Kp;
+    ctl[0] = kept;
+    ctl[1] = kept == (unsigned long long)Kp ? sortable_key(keys[Kp - 1]) : 0ull;
+  }
+}
+
+void select_begin(gpry_state* st, int Kp, int chunk_cands, cudaStream_t s) {
+  SelectRun& r = st->sel;
+  r.on = true;
+  r.Kp = Kp;
+  r.cur = 0;
+  r.pending = 0;
+  r.max_pending = 16;
+  r.cap = Kp + r.max_pending * chunk_cands;
+  for (int b = 0; b < 2; b++) {
+    st->sel_acq[b].reserve(r.cap);
+    st->sel_mean[b].reserve(r.cap);
+    st->sel_std[b].reserve(r.cap);
+    st->sel_idx[b].reserve(r.cap);
+  }
+  st->sel_ctl.reserve(4);
+  GPRY_CUDA(cudaMemsetAsync(st->sel_ctl.p, 0, 4 * sizeof(unsigned long long), s));
+}
+
+void select_compact(gpry_state* st, cudaStream_t s) {
+  SelectRun& r = st->sel;
+  if (r.pending == 0) return;
+  TimedScope ts(st, s, T_TOPK, 0);
+  const int Kp = r.Kp;
+  int64_t n = r.cap;
+  int64_t nblocks = (n + TK_E - 1) / TK_E;
+  for (int b = 0; b < 2; b++) {
+    st->tk_keys[b].reserve((size_t)nblocks * Kp);
+    st->tk_idx[b].reserve((size_t)nblocks * Kp);
+    st->tk_pos[b].reserve((size_t)nblocks * Kp);
+  }
+  const size_t smem = (size_t)TK_E * 20;
+  GPRY_CUDA(cudaFuncSetAttribute(topk_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  const double* kin = st->sel_acq[r.cur].p;
+  const int64_t* iin = st->sel_idx[r.cur].p;
+  const int* pin = nullptr;
+  const unsigned long long* cnt = st->sel_ctl.p;
+  int lvl = 0;
+  while (true) {
+    nblocks = (n + TK_E - 1) / TK_E;
+    topk_rec_kernel<<<(unsigned)nblocks, TK_THREADS, smem, s>>>(
+        kin, iin, pin, cnt, n, Kp, st->tk_keys[lvl].p, st->tk_idx[lvl].p, st->tk_pos[lvl].p);
+    GPRY_CUDA(cudaGetLastError());
+    st->n_launches += 1;
+    kin = st->tk_keys[lvl].p;
+    iin = st->tk_idx[lvl].p;
+    pin = st->tk_pos[lvl].p;
+    cnt = nullptr;
+    if (nblocks == 1) break;
+    n = nblocks * Kp;
+    lvl ^= 1;
+  }
+  const int o = r.cur ^ 1;
+  select_gather_kernel<<<1, 1024, 0, s>>>(kin, iin, pin, Kp, st->sel_acq[r.cur].p,
+                                          st->sel_mean[r.cur].p, st->sel_std[r.cur].p,
+                                          st->sel_acq[o].p, st->sel_idx[o].p, st->sel_mean[o].p,
+                                          st->sel_std[o].p, st->sel_ctl.p);
+  GPRY_CUDA(cudaGetLastError());
+  st->n_launches += 1;
+  r.cur = o;
+  r.pending = 0;
+}
+
+// final compaction; returns the number of records (<= K'), which sit sorted at the front of
+// sel_*[st->sel.cur].  Synchronises the stream.
+int64_t select_finish(gpry_state* st, cudaStream_t s) {
+  SelectRun& r = st->sel;
+  r.pending = std::max(r.pending, 1);
+  select_compact(st, s);
+  unsigned long long h[3] = {0, 0, 0};
+  GPRY_CUDA(cudaMemcpyAsync(h, st->sel_ctl.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  GPRY_CUDA(cudaStreamSynchronize(s));
+  r.on = false;
+  if (h[2] != 0)
+    throw GpryError{GPRY_ERR_STATE, "selection buffer overflow (internal error)"};
+  return (int64_t)h[0];
+}
+
+__global__ void gather_rows_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t idx_base,
+                                   const double* __restrict__ X, int d, double* __restrict__ o_X) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t g = idx[i] - idx_base;
+  for (int k = 0; k < d; k++) o_X[i * d + k] = X[g * d + k];
+}
+void gather_rows(gpry_state* st, const int64_t* d_idx, int64_t n, int64_t idx_base,
+                 const double* dX, int d, double* o_X, cudaStream_t s) {
+  if (n <= 0 || !o_X) return;
+  gather_rows_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_idx, n, idx_base, dX, d, o_X);
+  GPRY_CUDA(cudaGetLastError());
+  st->n_launches += 1;
 }
 
 __global__ void gather_topk_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t idx_base,

@@ -191,11 +191,22 @@ class DeviceGP:
                                             ptr(outs[2]), _stream_ptr(stream)))
         return tuple(outs)
 
+    def set_excluded(self, rows=None):
+        """Row numbers (sorted, within the pool given to the next ``predict_logexp_topk``
+        calls) that are skipped by the ranking; ``None`` clears the list."""
+        if rows is None or len(rows) == 0:
+            check(self._lib.gpry_set_excluded(self._h, None, 0))
+            return
+        rows = np.ascontiguousarray(np.sort(np.asarray(rows, dtype=np.int64)))
+        check(self._lib.gpry_set_excluded(self._h, ptr(rows), len(rows)))
+
     def predict_logexp_topk(self, X, zeta, sigma_n, y_max, Kp, idx_offset=0, stream=None,
-                            device_out=False, want_X=True):
+                            device_out=False, want_X=True, exclude=None):
         """The Kp best candidates by LogExp: (acq, idx, mean, std, X) sorted by descending
-        acq.  Only these records leave the GPU (``device_out``: they stay in torch tensors)."""
+        acq.  Only these records leave the GPU (``device_out``: they stay in torch tensors).
+        ``exclude``: rows of X left out of the ranking."""
         X, M, where = self._prep_X(X)
+        self.set_excluded(exclude)
         Kp = int(min(Kp, MAX_TOPK))
         n_out = C.c_int64(0)
         d = self.d

@@ -304,8 +304,10 @@ class NORA:
         self.mc_steps = mc_steps
         self.kprime = kprime
         self.verbose = verbose
-        self._X_mc = None
+        self._X_shard = None          # this rank's strided shard of the current MC sample
+        self._pool_given = None       # the object the sample came from (identity = same sample)
         self._X_already_proposed = np.empty((0, d))
+        self._idx_already_proposed = np.empty(0, dtype=np.int64)
         self.pool = None
         self.last_kprime = None
 
@@ -324,52 +326,99 @@ class NORA:
                                       "sampler) and 'ensemble'; or pass X_mc from your own")
         return rng.uniform(b[:, 0], b[:, 1], size=(self.nsamples, b.shape[0]))
 
+    # ------------------------------------------------------------------ the MC pool
+    def _set_pool(self, gpr, bounds, rng, force_resample, X_mc, X_shard):
+        """Decides whether this call works on a new MC sample (gp_acquisition.py:1016-1027) and
+        leaves this rank's strided shard in ``self._X_shard`` (row i of the shard is row
+        ``i * size + rank`` of the whole sample, mpi.py:114-115).  Nothing is pickled and the
+        whole sample never has to exist on one rank:
+
+        * ``X_shard``: every rank hands in its own shard (pageable numpy array, or a float64
+          torch CUDA tensor already resident on the rank's GPU) -- no communication at all;
+        * ``X_mc``: the whole sample, given on every rank (each keeps ``X_mc[rank::size]``), or
+          on rank 0 only (then the array is broadcast as a tensor, not as a pickled object);
+        * neither: rank 0 draws the sample with the built-in sampler and it is broadcast.
+        """
+        from . import parallel
+        rank, size = parallel.rank(), parallel.size()
+        given = X_shard if X_shard is not None else X_mc
+        same = given is not None and given is self._pool_given
+        new_sample = (force_resample or self._X_shard is None
+                      or (given is not None and not same)
+                      or (given is None and not bool(self.mc_every_i % self.mc_every)))
+        if not new_sample:
+            return False
+        if X_shard is not None:
+            shard = X_shard
+        else:
+            if X_mc is None and self.sampler is not None:
+                X_mc = self.do_MC_sample(gpr, bounds=bounds, rng=rng) \
+                    if parallel.is_main_process() else None
+            have = parallel.allgather(X_mc is not None) if size > 1 else [X_mc is not None]
+            if not have[0]:
+                raise ValueError("no MC sample: pass X_shard on every rank, or X_mc on every "
+                                 "rank or on rank 0")
+            if not all(have):
+                X_mc = parallel.bcast_array(X_mc)
+            shard = X_mc[rank::size] if size > 1 else X_mc
+        if not hasattr(shard, "is_cuda"):
+            shard = np.ascontiguousarray(shard, dtype=float)
+        self._X_shard = shard
+        self._pool_given = given
+        self._X_already_proposed = np.empty((0, gpr.d))
+        self._idx_already_proposed = np.empty(0, dtype=np.int64)
+        return True
+
     def multi_add(self, gpr, n_points=1, bounds=None, rng=None, force_resample=False,
-                  X_mc=None):
-        """gp_acquisition.py:971-1108 -> (X_pool, y_pool, acq_pool), identical on all ranks."""
+                  X_mc=None, X_shard=None):
+        """gp_acquisition.py:971-1108 -> (X_pool, y_pool, acq_pool), identical on all ranks.
+
+        One acquisition step: every rank scores its shard of the MC sample on its GPU
+        (mean, std, LogExp and the exact top-K' in one pass; rows proposed since the sample
+        was drawn are skipped on the device by index, :1037-1047), the per-rank survivor
+        lists are all-gathered, and every rank runs the same Kriging-believer ranking on
+        the best K' of the union -- which equals a single-process ranking of the whole
+        sample (see the module docstring for why the pre-selection is exact)."""
         from . import parallel
         if not (isinstance(n_points, int) and n_points > 0):
             raise ValueError(f"n_points should be int > 0, got {n_points}")
-        mc_this_time = not bool(self.mc_every_i % self.mc_every) or force_resample \
-            or self._X_mc is None or X_mc is not None
-        if mc_this_time:
-            if X_mc is None:
-                X_mc = self.do_MC_sample(gpr, bounds=bounds, rng=rng) \
-                    if parallel.is_main_process() else None
-                X_mc = parallel.bcast(X_mc)
-            self._X_mc = np.ascontiguousarray(X_mc, dtype=float)
-            self._X_already_proposed = np.empty((0, gpr.d))
+        rng = parallel.get_random_generator(rng)
+        self.last_new_sample = self._set_pool(gpr, bounds, rng, force_resample, X_mc, X_shard)
         self.mc_every_i += 1
-        X_all = self._X_mc
-        if self._X_already_proposed.size > 0:   # gp_acquisition.py:1037-1047
-            used = {row.tobytes() for row in self._X_already_proposed}
-            keep = np.array([row.tobytes() not in used for row in X_all])
-            X_all = X_all[keep]
+        rank, size = parallel.rank(), parallel.size()
+        this_X = self._X_shard
+        n_this = int(this_X.shape[0])
         zeta = self.acq_func.zeta
         noise = gpr.noise_level
         acq_func = partial(self.acq_func.f, baseline=gpr.y_max, noise_level=noise, zeta=zeta)
         self.acq_func_y_sigma = acq_func
-        # shard by stride (mpi.py:114-115), score + pre-rank on this rank's GPU
-        rank, size = parallel.rank(), parallel.size()
-        this_X = np.ascontiguousarray(X_all[rank::size])
+        done = self._idx_already_proposed
+        skip = np.sort(done[done % size == rank] // size) if len(done) else None
+        n_live = n_this - (0 if skip is None else len(skip))
         Kp = max(self.kprime, 4 * n_points)
         while True:
             Kp_eff = min(Kp, 2048)
-            if len(this_X):
-                a, i, m, s, Xs = gpr.predict_logexp_topk(this_X, zeta, Kp_eff)
+            if n_live > 0:
+                a, i, m, s, Xs = gpr.predict_logexp_topk(this_X, zeta, Kp_eff, exclude=skip)
+                a, i, m, s, Xs = (_to_numpy(v) for v in (a, i, m, s, Xs))
             else:
                 a, i, m, s, Xs = (np.empty(0), np.empty(0, dtype=np.int64), np.empty(0),
                                   np.empty(0), np.empty((0, gpr.d)))
-            local_cut = float(a[-1]) if (len(this_X) > Kp_eff and len(a)) else -np.inf
+            local_cut = float(a[-1]) if (n_live > Kp_eff and len(a)) else -np.inf
             i = i * size + rank       # position in the un-sharded sample
             a, i, m, s, Xs = parallel.allgather_survivors(a, i, m, s, Xs)
             order = np.lexsort((i, -a))
+            if len(order) > Kp_eff:
+                # Only the best K' of the union are ranked (keeps the posterior covariance at
+                # K' x K' whatever the number of ranks); the first row left out bounds what
+                # any dropped row could have scored, like a shard's own cut
+                local_cut = max(local_cut, float(a[order[Kp_eff]]))
+                order = order[:Kp_eff]
             a, i, m, s, Xs = a[order], i[order], m[order], s[order], Xs[order]
             pool = ranked_pool_from_scores(gpr, Xs, m, s, a, n_points, acq_func)
-            # Exactness of the pre-selection (module docstring): every candidate a truncated
-            # shard did NOT send has acq <= that shard's smallest survivor; if the largest such
-            # bound is <= the last-slot conditioned acq of a full pool, none of them could
-            # have entered.
+            # Exactness of the pre-selection (module docstring): every candidate that was NOT
+            # ranked has acq <= cut; if cut <= the last-slot conditioned acq of a full pool,
+            # none of them could have entered.
             cut = parallel.max_scalar(local_cut)
             if cut == -np.inf or (np.isfinite(pool.min_acq) and cut <= pool.min_acq) \
                     or Kp_eff >= 2048:
@@ -386,7 +435,16 @@ class NORA:
         with np.errstate(divide="ignore"):
             acq_pool = acq_func(y_pool, merged.sigma[:n_points])
         self._X_already_proposed = np.concatenate([self._X_already_proposed, X_pool])
+        self._idx_already_proposed = np.concatenate(
+            [self._idx_already_proposed, i[merged.idx[:len(X_pool)]]])
+        self.last_pool_idx = i[merged.idx[:len(X_pool)]]
         return X_pool, y_pool, acq_pool
+
+
+def _to_numpy(v):
+    if v is None or isinstance(v, np.ndarray):
+        return v
+    return v.detach().cpu().numpy()
 
 
 def _number_times_d(value, d, varname):

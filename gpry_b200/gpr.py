@@ -879,9 +879,11 @@ class GaussianProcessRegressor:
         return mean, std, acq
 
     def predict_logexp_topk(self, X, zeta, Kp, noise_level=None, idx_offset=0, stream=None,
-                            device_out=False, want_X=True):
+                            device_out=False, want_X=True, exclude=None):
         """Fused scoring + descending-acquisition pre-ranking: only the Kp best candidates
-        leave the GPU.  Returns (acq, idx, mean, std, X); masks as in ``predict_logexp``."""
+        leave the GPU.  Returns (acq, idx, mean, std, X); masks as in ``predict_logexp``.
+        ``exclude``: sorted row numbers of X that must not be returned (NORA's already
+        proposed points, gp_acquisition.py:1037-1047); they are skipped on the device."""
         self.n_eval += len(X)
         noise_level = self._scalar_noise(noise_level)
         dev = self._device_state()
@@ -890,10 +892,12 @@ class GaussianProcessRegressor:
         if rows is None:
             out = dev.predict_logexp_topk(X, zeta, noise_level, self.y_max, Kp,
                                           idx_offset=idx_offset, stream=stream,
-                                          device_out=device_out, want_X=want_X)
+                                          device_out=device_out, want_X=want_X, exclude=exclude)
             if self._clf_const is False:
                 out[0][:], out[2][:], out[3][:] = -np.inf, self.minus_inf_value, 0.0
             return out
+        if exclude is not None and len(exclude):
+            rows = np.setdiff1d(rows, np.asarray(exclude, dtype=np.int64))
         Xf = np.ascontiguousarray(np.asarray(X, dtype=float)[rows])
         if not len(rows):
             return (np.empty(0), np.empty(0, dtype=np.int64), np.empty(0), np.empty(0),

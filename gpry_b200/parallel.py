@@ -56,6 +56,38 @@ def bcast(obj, root=0):
     return box[0]
 
 
+def bcast_array(arr, root=0):
+    """Broadcast of a float64 array held by ``root`` as a TENSOR collective (shape first, then
+    the data over NCCL / gloo): no pickling, so it also carries MC samples of GB size, which
+    ``bcast`` (mpi.py:53-59 pickles through ``comm.bcast``) cannot."""
+    if not multiple_processes():
+        return arr
+    dev = _device()
+    meta = torch.zeros(9, dtype=torch.int64, device=dev)
+    if rank() == root:
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        meta[0] = arr.ndim
+        for k, n in enumerate(arr.shape):
+            meta[1 + k] = n
+    dist.broadcast(meta, src=root)
+    shape = tuple(int(n) for n in meta[1:1 + int(meta[0])].tolist())
+    t = torch.from_numpy(arr).to(dev) if rank() == root else \
+        torch.empty(shape, dtype=torch.float64, device=dev)
+    dist.broadcast(t, src=root)
+    return arr if rank() == root else t.cpu().numpy()
+
+
+def get_random_generator(seed=None):
+    """mpi.py:31-50: one independent ``Generator`` per rank, children of ONE ``SeedSequence``
+    (``spawn(SIZE)``; rank r gets child r).  Generators pass through.  With ``seed=None`` rank 0
+    draws the entropy and shares it, so the set of streams is still one family."""
+    if isinstance(seed, np.random.Generator):
+        return seed
+    if multiple_processes() and seed is None:
+        seed = bcast(np.random.SeedSequence().entropy if is_main_process() else None)
+    return np.random.default_rng(np.random.SeedSequence(seed).spawn(size())[rank()])
+
+
 def allgather(obj):
     """mpi.py:71-77."""
     if not multiple_processes():

@@ -166,11 +166,24 @@ int gpry_predict_logexp(gpry_state* st, const double* X, int64_t M, double zeta,
                         double* out_std, double* out_acq, void* stream);
 
 /*
+ * Rows that gpry_predict_logexp_topk must leave out of the ranking: NORA's already proposed
+ * points, which the reference deletes from the MC sample before scoring it
+ * (gp_acquisition.py:1037-1047).  rows: n strictly increasing row numbers within the pool X of
+ * the following calls (host pointer); n = 0 clears the list.  Stays set until changed.
+ */
+int gpry_set_excluded(gpry_state* st, const int64_t* rows, int n);
+
+/*
  * Fused scoring + ranking: the Kp candidates with the largest acquisition value, sorted by
  * descending acq (ties: ascending index; NaN ranks last).  idx are positions in X plus
  * idx_offset (so that shards report global indices).  out_X (Kp x d) may be NULL.
- * *n_out = min(Kp, M).  Output arrays are host or device per GPRY_OUT_ON_DEVICE and must
- * hold Kp entries; n_out is always a host pointer.
+ * *n_out = min(Kp, M - rows skipped by gpry_set_excluded).  Output arrays are host or device
+ * per GPRY_OUT_ON_DEVICE and must hold Kp entries; n_out is always a host pointer.
+ * The finishing kernel of every chunk of candidates keeps only the records whose acquisition
+ * value can still be among the Kp best (warp ballot + one atomic per warp against the running
+ * Kp-th best value; exact block sorts compact the survivors): the per-candidate mean / std /
+ * acquisition arrays are never written, only ranked candidates leave the GPU.  The call
+ * synchronises `stream` once (the number of survivors is data dependent).
  */
 int gpry_predict_logexp_topk(gpry_state* st, const double* X, int64_t M, double zeta,
                              double sigma_n, double y_max, int Kp, int64_t idx_offset,

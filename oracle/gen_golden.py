@@ -218,9 +218,88 @@ def loop_case(gpry):
     print("loop_banana_d2: acquired", np.array(acquired).shape, "final N", gpr.n)
 
 
+def bench_problem(N, d, seed=1234):
+    """The synthetic workload of bench.py / SURVEY.md 8(d) (same as oracle.synthetic_problem)."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(size=(N, d))
+    y = target(X)
+    ell = 0.5 if d <= 8 else (1.0 if d <= 16 else 1.5)
+    theta = np.log(np.concatenate([[1.0], np.full(d, ell)]))
+    return X, y, theta, np.array([[0.0, 1.0]] * d)
+
+
+def config_cases(gpry, which=("C", "D", "E")):
+    """Reference outputs AT THE SIZES of BASELINE.json configs[2], [3], [4] on bench.py's own
+    synthetic workload.  Only seeds + outputs are stored (inputs are regenerated)."""
+    from functools import partial
+    LogExp = gpry.acquisition_functions.LogExp
+    if "C" in which:   # N_train = 2000, d = 12, RBF: scores of 20000 candidates + ranked pool
+        N, d, M, n_points = 2000, 12, 20000, 12
+        X, y, theta, bounds = bench_problem(N, d)
+        gpr = make_reference_gpr(gpry, "rbf", X, y, theta, bounds)
+        Xc = np.random.default_rng(4321).uniform(size=(M, d))
+        mean, std = gpr.predict(Xc, return_std=True, validate=False)
+        zeta = d ** (-0.85)
+        acq_func = partial(LogExp.f, baseline=gpr.y_max, noise_level=gpr.noise_level, zeta=zeta)
+        with np.errstate(divide="ignore"):
+            acq = acq_func(mean, std)
+            rp = gpry.gp_acquisition.RankedPool(n_points, gpr=gpr, acq_func=acq_func, verbose=0)
+            rp.add(Xc, mean, std, acq, method="single sort acq")
+            rp = rp.copy(drop_empty=True)
+        idx = np.array([int(np.flatnonzero(np.all(Xc == x, axis=1))[0]) for x in rp.X[:n_points]])
+        np.savez_compressed(
+            os.path.join(OUT, "config_c_n2000_d12.npz"), N=N, d=d, M=M, seed=1234, cand_seed=4321,
+            theta=theta, zeta=zeta, noise_level=1e-2, mean=mean, std=std, acq=acq,
+            y_mean=gpr.preprocessing_y.mean_, y_std=gpr.preprocessing_y.std_, y_max=gpr.y_max,
+            pool_n_points=n_points, pool_idx=idx, pool_y=rp.y[:n_points],
+            pool_sigma=rp.sigma[:n_points], pool_acq_cond=rp.acq_cond[:n_points],
+            alpha_head=gpr.alpha_[:16], L_diag=np.diag(gpr.L_), condK=np.linalg.cond(gpr.L_) ** 2)
+        print("config_c: cond(K)=%.3g std [%.3g, %.3g] pool idx %s" % (
+            np.linalg.cond(gpr.L_) ** 2, std.min(), std.max(), idx))
+    if "D" in which:   # N_train = 4000, d = 20: LML + gradient at restart points
+        N, d = 4000, 20
+        X, y, theta, bounds = bench_problem(N, d)
+        rng = np.random.default_rng(7)
+        out = dict(N=N, d=d, seed=1234, noise_level=1e-2)
+        for kind in ("rbf", "matern25"):
+            gpr = make_reference_gpr(gpry, kind, X[:64], y[:64], theta, bounds)
+            # the LML only needs the training set in the transformed space and alpha
+            from gpry.preprocessing import Normalize_y
+            py = Normalize_y()
+            py.fit(X, y)
+            gpr.X_train_ = X.copy()          # bounds [0, 1]^d: Normalize_bounds is the identity
+            gpr.y_train_ = py.transform(y)
+            gpr.alpha = np.full(N, (1e-2 / py.std_) ** 2)
+            lo, hi = gpr.kernel_.bounds[:, 0], gpr.kernel_.bounds[:, 1]
+            thetas = [theta, theta + 0.1 * rng.standard_normal(d + 1)]
+            if kind == "rbf":     # one start drawn like fit_gpr_hyperparameters does (gpr.py:976)
+                thetas.append(rng.uniform(lo, hi))
+            lml, grad = [], []
+            for th in thetas:
+                v, g = gpr.log_marginal_likelihood(th, eval_gradient=True, clone_kernel=True)
+                lml.append(v), grad.append(g)
+                print(f"config_d {kind}: lml {v:.12g}  |grad| {np.abs(g).max():.4g}")
+            out.update({f"thetas_{kind}": np.array(thetas), f"lml_{kind}": np.array(lml),
+                        f"grad_{kind}": np.array(grad)})
+        np.savez_compressed(os.path.join(OUT, "config_d_n4000_d20.npz"), **out)
+    if "E" in which:   # N_train = 2000, d = 16: mean only (surrogate-MCMC proposals)
+        N, d, M = 2000, 16, 20000
+        X, y, theta, bounds = bench_problem(N, d)
+        gpr = make_reference_gpr(gpry, "rbf", X, y, theta, bounds)
+        Xc = np.random.default_rng(4321).uniform(size=(M, d))
+        mean = gpr.predict(Xc, validate=False)
+        np.savez_compressed(os.path.join(OUT, "config_e_n2000_d16.npz"), N=N, d=d, M=M, seed=1234,
+                            cand_seed=4321, theta=theta, noise_level=1e-2, mean=mean,
+                            y_std=gpr.preprocessing_y.std_, condK=np.linalg.cond(gpr.L_) ** 2)
+        print("config_e: mean range [%.4g, %.4g]" % (mean.min(), mean.max()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gpry = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "configs":
+        config_cases(gpry, tuple(sys.argv[2:]) or ("C", "D", "E"))
+        return
     case(gpry, "rbf_d2_n60", "rbf", 60, 2, 128, 11, 0.3, pool=(4000, 4))
     case(gpry, "rbf_d8_n300", "rbf", 300, 8, 256, 12, 0.5, pool=(20000, 8))
     case(gpry, "matern25_d8_n300", "matern25", 300, 8, 256, 13, 0.8)
@@ -239,6 +318,7 @@ def main():
     nonpd_case(gpry)
     fit_case(gpry)
     loop_case(gpry)
+    config_cases(gpry)
 
 
 def extra_cases(gpry):

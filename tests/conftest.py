@@ -19,7 +19,7 @@ def pytest_configure(config):
 def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0]
                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith(("lml_nonpd", "fit_", "loop_")))
+                  if not os.path.basename(p).startswith(("lml_nonpd", "fit_", "loop_", "config_")))
 
 
 def load_golden(name):

@@ -164,10 +164,13 @@ class FakeDeviceGP:
         return mean, std, acq
 
     def predict_logexp_topk(self, X, zeta, sigma_n, y_max, Kp, idx_offset=0, stream=None,
-                            device_out=False, want_X=True):
+                            device_out=False, want_X=True, exclude=None):
         mean, std, acq = self.predict_logexp(X, zeta, sigma_n, y_max)
         key = np.where(np.isnan(acq), -np.inf, acq)
-        order = np.lexsort((np.arange(len(acq)), -key))[:Kp]
+        order = np.lexsort((np.arange(len(acq)), -key))
+        if exclude is not None and len(exclude):
+            order = order[~np.isin(order, exclude)]
+        order = order[:Kp]
         return (acq[order], order.astype(np.int64) + idx_offset, mean[order], std[order],
                 np.asarray(X)[order] if want_X else None)
 

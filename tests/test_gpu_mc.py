@@ -71,8 +71,8 @@ def test_nora_with_ensemble_sampler():
     nora = NORA(bounds, sampler="ensemble", nsamples=20001, mc_steps=60, verbose=0)
     X, y, acq = nora.multi_add(gpr, n_points=3, rng=np.random.default_rng(0))
     assert X.shape == (3, 3) and np.all(np.isfinite(acq))
-    assert nora._X_mc.shape == (20001, 3)
+    assert nora._X_shard.shape == (20001, 3)
     # the pool is drawn where the surrogate posterior has mass, not uniformly in the box
-    assert np.all(np.abs(nora._X_mc.mean(axis=0) - 0.5) < 0.05)
-    assert np.all(nora._X_mc.std(axis=0) < 0.2)
+    assert np.all(np.abs(nora._X_shard.mean(axis=0) - 0.5) < 0.05)
+    assert np.all(nora._X_shard.std(axis=0) < 0.2)
     assert np.all(np.linalg.norm(X - 0.5, axis=1) < 0.6)

@@ -168,6 +168,21 @@ def test_acquisition_engines_on_fake_device(monkeypatch):
     nora = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=64)
     X_pool, y_pool, acq_pool = nora.multi_add(gpr, n_points=int(g["pool_n_points"]), X_mc=Xp)
     assert np.array_equal(X_pool, Xp[g["pool_idx_single_sort_acq"]])
+    assert np.array_equal(nora.last_pool_idx, g["pool_idx_single_sort_acq"])
+    # the same sample again (same object): the rows proposed above are skipped by index, and
+    # the result is the ranking of the sample without them (gp_acquisition.py:1037-1047)
+    X2, _, _ = nora.multi_add(gpr, n_points=int(g["pool_n_points"]), X_mc=Xp)
+    assert not nora.last_new_sample
+    assert not set(map(bytes, X2)) & set(map(bytes, X_pool))
+    fresh = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=64)
+    X2_ref, _, _ = fresh.multi_add(gpr, n_points=int(g["pool_n_points"]),
+                                   X_mc=np.delete(Xp, g["pool_idx_single_sort_acq"], axis=0))
+    assert np.array_equal(X2, X2_ref)
+    assert len(nora._X_already_proposed) == 2 * int(g["pool_n_points"])
+    # a sharded hand-over (what every rank of a multi-GPU run does) gives the same pool
+    sharded = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=64)
+    X3, _, _ = sharded.multi_add(gpr, n_points=int(g["pool_n_points"]), X_shard=Xp)
+    assert np.array_equal(X3, X_pool)
     opt = BatchOptimizer(g["bounds"], preprocessing_X=Normalize_bounds(g["bounds"]),
                          acq_func=LogExp(zeta=g["zeta"]), n_restarts_optimizer=4, verbose=0)
     n0 = gpr.n

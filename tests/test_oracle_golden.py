@@ -96,3 +96,52 @@ def test_ranked_pool(golden, method):
     tag = method.replace(" ", "_")
     assert np.array_equal(idx, g[f"pool_idx_{tag}"])
     assert scaled_err(ys, g[f"pool_y_{tag}"], float(g["y_std"])) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE.json config sizes (reference-minted on bench.py's synthetic workload;
+# oracle/gen_golden.py config_cases): the oracle is pinned where the benchmarks run
+# ---------------------------------------------------------------------------------------
+def test_config_c_scores_and_pool():
+    z = np.load(os.path.join(GOLDEN_DIR, "config_c_n2000_d12.npz"))
+    N, d, M = int(z["N"]), int(z["d"]), int(z["M"])
+    X, y, theta, bounds = orc.synthetic_problem(N, d, seed=int(z["seed"]))
+    assert np.array_equal(theta, z["theta"])
+    st = orc.GPState("rbf", theta, X, y, bounds=bounds)
+    Xc = np.random.default_rng(int(z["cand_seed"])).uniform(size=(M, d))
+    sy = float(z["y_std"])
+    sub = slice(0, 6000)
+    mean, std, acq = orc.predict_logexp(st, Xc[sub], zeta=float(z["zeta"]))
+    assert scaled_err(mean, z["mean"][sub], sy) < TOL
+    assert scaled_err(std ** 2, z["std"][sub] ** 2, sy ** 2) < TOL
+    assert scaled_err(acq, z["acq"][sub], 1.0) < 1e-9
+    assert scaled_err(np.diag(st.L_), z["L_diag"], 1.0) < 1e-12
+    # the ranked pool from the reference's own scores (the oracle's refits at N = 2000)
+    idx, Xs, ys, acqs = orc.ranked_pool_select(st, Xc, z["mean"], z["std"], z["acq"],
+                                               int(z["pool_n_points"]), zeta=float(z["zeta"]))
+    assert np.array_equal(idx, z["pool_idx"])
+
+
+def test_config_d_lml():
+    z = np.load(os.path.join(GOLDEN_DIR, "config_d_n4000_d20.npz"))
+    N, d = int(z["N"]), int(z["d"])
+    X, y, _, _ = orc.synthetic_problem(N, d, seed=int(z["seed"]))
+    y_mean, y_std = orc.normalize_y_fit(y)
+    y_ = (y - y_mean) / y_std
+    noise2 = np.full(N, (float(z["noise_level"]) / y_std) ** 2)
+    for kind, pick in (("rbf", 1), ("matern25", 0)):      # (all of them: GPU test_gpu_configs.py)
+        for th, v, gr in zip(z[f"thetas_{kind}"][pick:pick + 1], z[f"lml_{kind}"][pick:],
+                             z[f"grad_{kind}"][pick:]):
+            lml, grad = orc.log_marginal_likelihood(kind, th, X, y_, noise2, eval_gradient=True)
+            assert abs(lml - v) <= 1e-11 * abs(v), (kind, lml, v)
+            assert scaled_err(grad, gr, np.abs(gr).max()) < 1e-10
+
+
+def test_config_e_mean_only():
+    z = np.load(os.path.join(GOLDEN_DIR, "config_e_n2000_d16.npz"))
+    N, d, M = int(z["N"]), int(z["d"]), int(z["M"])
+    X, y, theta, bounds = orc.synthetic_problem(N, d, seed=int(z["seed"]))
+    st = orc.GPState("rbf", theta, X, y, bounds=bounds)
+    Xc = np.random.default_rng(int(z["cand_seed"])).uniform(size=(M, d))
+    mean = orc.predict(st, Xc[:8000])
+    assert scaled_err(mean, z["mean"][:8000], float(z["y_std"])) < TOL

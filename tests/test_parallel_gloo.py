@@ -41,9 +41,12 @@ class FakeDeviceGPR:
     def predict_std(self, X, validate=True):
         return orc.predict_std(self.st, X)
 
-    def predict_logexp_topk(self, X, zeta, Kp, **kw):
+    def predict_logexp_topk(self, X, zeta, Kp, exclude=None, **kw):
         m, s, a = orc.predict_logexp(self.st, X, zeta=zeta)
-        order = np.lexsort((np.arange(len(a)), -a))[:Kp]
+        order = np.lexsort((np.arange(len(a)), -a))
+        if exclude is not None and len(exclude):
+            order = order[~np.isin(order, exclude)]
+        order = order[:Kp]
         return a[order], order.astype(np.int64), m[order], s[order], X[order]
 
     def _device_state(self):
@@ -77,6 +80,12 @@ class FakeDeviceGPR:
         Ks = orc.kernel_cross(self.st.kind, self.st.theta, X_, self.st.X_train_)
         U = self.st.V_ @ Ks.T
         return orc.kernel_cross(self.st.kind, self.st.theta, X_, X_) - U.T @ U
+
+
+def orc_ranked_rows(gpr, X, n_points, zeta):
+    """Single-process reference ranking of a whole sample (oracle arithmetic)."""
+    m, s, a = orc.predict_logexp(gpr.st, X, zeta=zeta)
+    return orc.ranked_pool_select(gpr.st, X, m, s, a, n_points, zeta=zeta)[1]
 
 
 def _free_port():
@@ -136,6 +145,34 @@ def _worker(rank, world, port, out_dir):
     X_pool, y_pool, acq_pool = nora.multi_add(gpr, n_points=n_points, X_mc=Xp)
     assert np.array_equal(X_pool, Xp[g["pool_idx_single_sort_acq"]])
     np.save(os.path.join(out_dir, f"pool_{rank}.npy"), X_pool)
+    # sharded hand-over: every rank gives only ITS rows (no broadcast of the sample); second call
+    # on the same shards skips the rows proposed by the first (by global index, on every rank)
+    nora_s = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=64)
+    shard = np.ascontiguousarray(Xp[rank::world])
+    Xs1, _, _ = nora_s.multi_add(gpr, n_points=n_points, X_shard=shard)
+    assert np.array_equal(Xs1, X_pool)
+    assert np.array_equal(nora_s.last_pool_idx, g["pool_idx_single_sort_acq"])
+    Xs2, _, _ = nora_s.multi_add(gpr, n_points=n_points, X_shard=shard)
+    assert not nora_s.last_new_sample
+    assert not set(map(bytes, Xs2)) & set(map(bytes, Xs1))
+    one = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=64)
+    ref2 = orc_ranked_rows(gpr, np.delete(Xp, g["pool_idx_single_sort_acq"], axis=0), n_points,
+                           g["zeta"])
+    assert np.array_equal(Xs2, ref2)
+    # X_mc held by rank 0 only: tensor broadcast, no pickle
+    nora_b = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=64)
+    Xb1, _, _ = nora_b.multi_add(gpr, n_points=n_points, X_mc=Xp if rank == 0 else None)
+    assert np.array_equal(Xb1, X_pool)
+    # K' small and many ranks' worth of survivors: only the best K' of the union are ranked
+    # (the posterior covariance stays K' x K'), the exactness bound still holds
+    nora_k = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=16)
+    Xk, _, _ = nora_k.multi_add(gpr, n_points=n_points, X_shard=shard)
+    assert np.array_equal(Xk, X_pool)
+    # per-rank generators: children of one SeedSequence (mpi.py:31-50)
+    r1 = parallel.get_random_generator(123).uniform()
+    both = parallel.allgather(r1)
+    assert both[0] != both[1]
+    assert both[rank] == np.random.default_rng(np.random.SeedSequence(123).spawn(world)[rank]).uniform()
     # BatchOptimizer: restarts split over the ranks (mpi.split_number_for_parallel_processes,
     # gp_acquisition.py:454-458), results gathered, every rank picks the same optimum and
     # appends the same lie
