@@ -39,6 +39,8 @@ SIGNATURES = {
     "gpry_predict_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "gpry_set_contract_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "gpry_set_contract_guard": (C.c_int, [C.c_void_p, C.c_int]),
+    "gpry_contract_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gpry_int8_peak": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gpry_set_mask_value": (C.c_int, [C.c_void_p, C.c_double]),
     "gpry_set_classifier": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -74,6 +76,16 @@ SIGNATURES = {
     "gpry_lml_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    "gpry_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "gpry_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "gpry_comm_share": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gpry_comm_destroy": (C.c_int, [C.c_void_p]),
+    "gpry_comm_info": (C.c_int, [C.c_void_p, _c_int_p, _c_int_p, _c_int_p]),
+    "gpry_bcast_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "gpry_allgather_topk": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      _c_int64_p, _c_double_p, C.c_void_p]),
     "gpry_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gpry_get_timings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
 }

@@ -112,33 +112,43 @@ static void run_pipeline_blocks(gpry_state* st, const double* X, int64_t M, bool
   *dX_out = st->Xdev.p;
   const int nblocks = (int)((M + block - 1) / block);
   if (nblocks <= 1) {
-    TimedScope ts(st, s, T_H2D, 0);
-    GPRY_CUDA(cudaMemcpyAsync(st->Xdev.p, X, (size_t)M * d * 8, cudaMemcpyHostToDevice, s));
-  } else {
-    if (!st->copy_stream)
-      GPRY_CUDA(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
-    if (!st->call_start)
-      GPRY_CUDA(cudaEventCreateWithFlags(&st->call_start, cudaEventDisableTiming));
-    while ((int)st->copy_events.size() < nblocks) {
-      cudaEvent_t e;
-      GPRY_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      st->copy_events.push_back(e);
+    {
+      TimedScope ts(st, s, T_H2D, 0);
+      GPRY_CUDA(cudaMemcpyAsync(st->Xdev.p, X, (size_t)M * d * 8, cudaMemcpyHostToDevice, s));
     }
-    // the staging buffer may still be read by work queued earlier on the compute stream
-    GPRY_CUDA(cudaEventRecord(st->call_start, s));
-    GPRY_CUDA(cudaStreamWaitEvent(st->copy_stream, st->call_start, 0));
-    for (int b = 0; b < nblocks; b++) {
-      const int64_t off = b * block, n = std::min(block, M - off);
-      GPRY_CUDA(cudaMemcpyAsync(st->Xdev.p + off * d, X + off * d, (size_t)n * d * 8,
-                                cudaMemcpyHostToDevice, st->copy_stream));
-      GPRY_CUDA(cudaEventRecord(st->copy_events[b], st->copy_stream));
-    }
+    run_block(st, st->Xdev.p, 0, M, want_var, want_acq, zeta, sigma_n, y_max, dm, ds, da,
+              idx_offset, s);
+    return;
   }
+  if (!st->copy_stream)
+    GPRY_CUDA(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
+  if (!st->call_start)
+    GPRY_CUDA(cudaEventCreateWithFlags(&st->call_start, cudaEventDisableTiming));
+  while ((int)st->copy_events.size() < nblocks) {
+    cudaEvent_t e;
+    GPRY_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    st->copy_events.push_back(e);
+  }
+  // the staging buffer may still be read by work queued earlier on the compute stream
+  GPRY_CUDA(cudaEventRecord(st->call_start, s));
+  GPRY_CUDA(cudaStreamWaitEvent(st->copy_stream, st->call_start, 0));
+  auto enqueue_copy = [&](int b) {
+    const int64_t off = b * block, n = std::min(block, M - off);
+    GPRY_CUDA(cudaMemcpyAsync(st->Xdev.p + off * d, X + off * d, (size_t)n * d * 8,
+                              cudaMemcpyHostToDevice, st->copy_stream));
+    GPRY_CUDA(cudaEventRecord(st->copy_events[b], st->copy_stream));
+  };
+  // The copy of block b + 1 is enqueued right AFTER the kernels of block b: from pageable host
+  // memory cudaMemcpyAsync returns only once the block has been staged, and while the host
+  // waits there the GPU works through block b, so the transfer stays hidden for pageable as
+  // for pinned buffers; only the copy of block 0 is exposed.
+  enqueue_copy(0);
   for (int b = 0; b < nblocks; b++) {
     const int64_t off = b * block, n = std::min(block, M - off);
-    if (nblocks > 1) GPRY_CUDA(cudaStreamWaitEvent(s, st->copy_events[b], 0));
+    GPRY_CUDA(cudaStreamWaitEvent(s, st->copy_events[b], 0));
     run_block(st, st->Xdev.p + off * d, off, n, want_var, want_acq, zeta, sigma_n, y_max, dm, ds,
               da, idx_offset, s);
+    if (b + 1 < nblocks) enqueue_copy(b + 1);
   }
 }
 
@@ -201,7 +211,10 @@ int gpry_state_destroy(gpry_state* st) {
     st->VTrm.release(); st->gr_out.release(); st->clf_dec.release();
     for (int b = 0; b < 2; b++) { st->sel_acq[b].release(); st->sel_mean[b].release(); st->sel_std[b].release(); st->sel_idx[b].release(); st->tk_pos[b].release(); }
     st->sel_ctl.release(); st->excl.release();
-    st->oz_Ksl.release(); st->oz_Vs.release(); st->oz_scale.release(); st->oz_rb.release(); st->oz_park.release();
+    st->oz_probe.release(); st->oz_Ksl.release(); st->oz_Vs.release(); st->oz_scale.release(); st->oz_rb.release(); st->oz_park.release();
+    comm_destroy(st);
+    st->cm_hdr.release(); st->cm_send.release(); st->cm_recv.release(); st->mg_keys.release();
+    st->mg_idx.release();
     if (st->clf) gpry_state_destroy(st->clf);
     st->f_K.release(); st->f_VT.release(); st->f_W.release(); st->f_TT.release();
     st->f_Winv.release(); st->f_misc.release(); st->f_prob.release();
@@ -267,6 +280,35 @@ int gpry_set_contract_mode(gpry_state* st, int mode) {
     GPRY_CHECK_ARG(st != nullptr, "state is NULL");
     GPRY_CHECK_ARG(mode >= GPRY_CONTRACT_FP64 && mode <= GPRY_CONTRACT_INT8_1PASS, "unknown mode");
     st->contract_mode = mode;
+  });
+}
+
+int gpry_set_contract_guard(gpry_state* st, int enable) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    st->oz_guard = enable != 0;
+    st->oz_checked = false;
+  });
+}
+
+int gpry_contract_info(gpry_state* st, double* out8) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && out8, "NULL argument");
+    if (!st->loaded) throw GpryError{GPRY_ERR_STATE, "no model uploaded into this state"};
+    GPRY_CUDA(cudaSetDevice(st->device));
+    const bool eligible = st->contract_mode != 0 && st->has_V && st->Npad >= 512 && st->Npad <= 16384;
+    if (eligible) {        // evaluate the guard now if no scoring call has done it yet
+      ozaki_prepare(st, 0);
+      ozaki_validate(st, 0);
+    }
+    out8[0] = st->contract_mode;
+    out8[1] = (eligible && ozaki_supported(st)) ? st->contract_mode : GPRY_CONTRACT_FP64;
+    out8[2] = eligible ? st->oz_est_sigma : 0.0;
+    out8[3] = eligible ? st->oz_bound_worst : 0.0;
+    out8[4] = eligible ? st->oz_probe_err : -1.0;
+    out8[5] = OZ_TOLERANCE;
+    out8[6] = st->oz_guard ? 1.0 : 0.0;
+    out8[7] = 0.0;
   });
 }
 
@@ -581,6 +623,63 @@ int gpry_lml_batched(gpry_state* st, int kind, int N, int d, const double* X_tra
     GPRY_CHECK_ARG(B >= 1, "B < 1");
     lml_batched_device(st, kind, N, d, X_train_t, noise2, y_t, thetas, B, out_lml, out_grad,
                        out_info);
+  });
+}
+
+int gpry_comm_unique_id(void* out128) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(out128 != nullptr, "NULL argument");
+    comm_unique_id(out128);
+  });
+}
+
+int gpry_comm_init(gpry_state* st, const void* id128, int rank, int nranks) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st && id128, "NULL argument");
+    comm_init(st, id128, rank, nranks);
+  });
+}
+
+int gpry_comm_share(gpry_state* dst, gpry_state* src) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(dst && src, "NULL argument");
+    comm_share(dst, src);
+  });
+}
+
+int gpry_comm_destroy(gpry_state* st) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    comm_destroy(st);
+  });
+}
+
+int gpry_comm_info(const gpry_state* st, int* rank, int* nranks, int* nccl_version) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    if (rank) *rank = st->comm_rank;
+    if (nranks) *nranks = st->comm ? st->comm_size : 0;
+    if (nccl_version) *nccl_version = comm_nccl_version();
+  });
+}
+
+int gpry_bcast_state(gpry_state* st, int root, void* stream) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    bcast_state(st, root, (cudaStream_t)stream);
+  });
+}
+
+int gpry_allgather_topk(gpry_state* st, int n_local, int Kp, int d, const double* acq,
+                        const int64_t* idx, const double* mean, const double* std_,
+                        const double* X, int where, double* out_acq, int64_t* out_idx,
+                        double* out_mean, double* out_std, double* out_X, int64_t* n_out,
+                        double* next_acq, void* stream) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr, "state is NULL");
+    allgather_topk(st, n_local, Kp, d, acq, idx, mean, std_, X, where & GPRY_X_ON_DEVICE,
+                   where & GPRY_OUT_ON_DEVICE, out_acq, out_idx, out_mean, out_std, out_X, n_out,
+                   next_acq, (cudaStream_t)stream);
   });
 }
 

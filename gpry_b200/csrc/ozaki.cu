@@ -393,17 +393,28 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
 }
 
 // per row of V (row-major, padded to Np): 2^e with |V_jk| / 2^e < 1
+// row_stat[j] = |V_j|_2^2 + 4^e_j (j + 1): what the a-priori error estimate of the split needs
 __global__ void __launch_bounds__(256)
-oz_row_exponent_kernel(const double* __restrict__ Vrm, int Np, double* __restrict__ row_pow2) {
+oz_row_exponent_kernel(const double* __restrict__ Vrm, int Np, double* __restrict__ row_pow2,
+                       double* __restrict__ row_stat) {
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (j >= Np) return;
-  double mx = 0.0;
-  for (int k = lane; k <= j; k += 32) mx = fmax(mx, fabs(Vrm[(size_t)j * Np + k]));
-  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  double mx = 0.0, ss = 0.0;
+  for (int k = lane; k <= j; k += 32) {
+    const double v = Vrm[(size_t)j * Np + k];
+    mx = fmax(mx, fabs(v));
+    ss = fma(v, v, ss);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
   if (lane == 0) {
     int e = 0;
     if (mx > 0.0) frexp(mx, &e);       // mx = m 2^e, m in [0.5, 1)
-    row_pow2[j] = ldexp(1.0, e);
+    const double p2 = ldexp(1.0, e);
+    row_pow2[j] = p2;
+    row_stat[j] = mx > 0.0 ? ss + p2 * p2 * (double)(j + 1) : 0.0;
   }
 }
 // digits of V: thread per (row j, 16 consecutive k); layout [row block][k chunk of 32][slice]
@@ -536,7 +547,30 @@ double ozaki_int8_peak_tops(gpry_state* st) {
 }
 
 bool ozaki_supported(const gpry_state* st) {
-  return st->has_V && st->Npad >= 512 && st->Npad <= 16384;
+  if (!(st->has_V && st->Npad >= 512 && st->Npad <= 16384)) return false;
+  // the guard (ozaki_prepare + ozaki_validate) has ruled the split out for this model
+  return !(st->oz_guard && st->oz_valid && st->oz_checked && !st->oz_ok);
+}
+
+// A-priori error model of the split.  Operands are rounded to 55-bit fixed
+// point: k*_k / c to a multiple of 2^-54 and V_jk to a multiple of 2^(e_j - 54); digit groups
+// g >= 7 of the product are dropped.  For the row product w_j = sum_k V_jk k*_k over n_j = j + 1
+// terms:
+//   worst case   |dw_j| <= c 2^e_j n_j (1 + 6.02) 2^-54              (all errors aligned)
+//   statistical  sd(dw_j) ~= 2.2 c 2^-55 sqrt((|V_j|_2^2 + 4^e_j n_j) / 3)
+//                (independent uniform roundings of both operands, rho = rms(k* / c) <= 1;
+//                 the dropped groups add about as much again: factor 2.2)
+// and for the variance c - sum_j w_j^2 (sum_j w_j^2 <= c):  d var <= 2 sqrt(c) max_j |dw_j|.
+static void ozaki_error_model(gpry_state* st, const std::vector<double>& row_stat,
+                              const std::vector<double>& row_pow2) {
+  double worst = 0.0, stat = 0.0;
+  for (int j = 0; j < st->N; j++) {
+    worst = std::max(worst, row_pow2[j] * (double)(j + 1));
+    stat = std::max(stat, row_stat[j]);
+  }
+  const double c = st->c, eps = ldexp(1.0, -54);
+  st->oz_bound_worst = 2.0 * sqrt(c) * c * worst * 7.02 * eps;
+  st->oz_est_sigma = 2.0 * sqrt(c) * 2.2 * c * 0.5 * eps * sqrt(stat / 3.0);
 }
 
 // digits of V and the balanced assignment of row blocks to row splits (once per upload and
@@ -546,9 +580,10 @@ void ozaki_prepare(gpry_state* st, cudaStream_t s) {
   if (st->oz_valid && st->oz_rows == rows) return;
   const int Np = st->Npad, nRB = Np / rows, nKC = Np / OZ_KC;
   st->oz_Vs.reserve((size_t)nRB * nKC * OZ_NS * rows * OZ_KC);
-  st->oz_scale.reserve(2 * (size_t)Np);
+  st->oz_scale.reserve(3 * (size_t)Np);
   double* row_pow2 = st->oz_scale.p + Np;
-  oz_row_exponent_kernel<<<(Np + 7) / 8, 256, 0, s>>>(st->Vrm.p, Np, row_pow2);
+  double* row_stat = st->oz_scale.p + 2 * (size_t)Np;
+  oz_row_exponent_kernel<<<(Np + 7) / 8, 256, 0, s>>>(st->Vrm.p, Np, row_pow2, row_stat);
   GPRY_CUDA(cudaGetLastError());
   const int64_t tot = (int64_t)Np * (Np / 16);
   oz_slice_v_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(st->Vrm.p, Np, row_pow2, rows,
@@ -594,7 +629,11 @@ void ozaki_prepare(gpry_state* st, cudaStream_t s) {
   st->oz_rb.reserve(h.size());
   GPRY_CUDA(cudaMemcpyAsync(st->oz_rb.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, s));
   if (rows == OZ2_ROWS) st->oz_park.reserve((size_t)OZ2_PARK_SLOTS * OZ2_ROWS * TILE_ROWS);
+  std::vector<double> h_stat(2 * (size_t)Np);
+  GPRY_CUDA(cudaMemcpyAsync(h_stat.data(), row_pow2, 2 * (size_t)Np * 8, cudaMemcpyDeviceToHost, s));
   GPRY_CUDA(cudaStreamSynchronize(s));
+  ozaki_error_model(st, std::vector<double>(h_stat.begin() + Np, h_stat.end()),
+                    std::vector<double>(h_stat.begin(), h_stat.begin() + Np));
   st->oz_splits = splits;
   st->oz_max_rb = max_rb;
   st->oz_rows = rows;
@@ -603,6 +642,9 @@ void ozaki_prepare(gpry_state* st, cudaStream_t s) {
   GPRY_CUDA(cudaFuncSetAttribute(oz2_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)OZ2_SMEM));
   st->oz_valid = true;
+  st->oz_checked = false;      // ozaki_validate (predict.cu) decides before the first use
+  st->oz_ok = true;
+  st->oz_probe_err = -1.0;
 }
 
 size_t ozaki_kslices_bytes(const gpry_state* st, int tiles) {

@@ -1095,8 +1095,12 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
   const int chunk_tiles = (int)std::min<int64_t>(total_tiles, max_chunk_tiles);
   const int chunk_cands = chunk_tiles * TILE_ROWS;
   // INT8 split of the contraction (ozaki.cu) when selected and the model qualifies
-  const bool ozaki = want_var && st->contract_mode != 0 && ozaki_supported(st);
-  if (ozaki) ozaki_prepare(st, s);
+  bool ozaki = want_var && st->contract_mode != 0 && ozaki_supported(st);
+  if (ozaki) {
+    ozaki_prepare(st, s);
+    ozaki_validate(st, s);      // error model + probe against the FP64 kernel, once per model
+    ozaki = ozaki_supported(st);
+  }
   // row splits: for small pools spread the row blocks of V over more CTAs
   int row_splits = 1;
   if (ozaki) {
@@ -1183,6 +1187,82 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
       GPRY_CUDA(cudaGetLastError());
     }
   }
+}
+
+// Guard of the INT8 split, once per uploaded model (and digit layout): (1) the a-priori
+// statistical estimate of ozaki.cu must be below the tolerance, (2) on 512 probe candidates --
+// 256 training points (smallest variances, largest cancellation in c - sum w^2, taken evenly
+// from all row blocks of V) and 256 uniform draws from the training set's bounding box -- the
+// INT8 and the FP64 (DMMA) contraction must agree to tolerance / 16.  Otherwise this model
+// takes the FP64 kernel (st->oz_ok = false).
+void ozaki_validate(gpry_state* st, cudaStream_t s) {
+  if (st->oz_checked) return;
+  st->oz_checked = true;         // also stops the recursion: the probe runs predict_pipeline
+  st->oz_ok = true;
+  st->oz_probe_err = -1.0;
+  if (!st->oz_guard) return;
+  if (!(st->oz_est_sigma <= OZ_TOLERANCE)) {
+    st->oz_ok = false;
+    return;
+  }
+  const int P = 512, d = st->d, N = st->N;
+  std::vector<double> Xt((size_t)N * d), prm(3 * MAX_DIM), probe((size_t)P * d);
+  GPRY_CUDA(cudaMemcpyAsync(Xt.data(), st->Xt.p, (size_t)N * d * 8, cudaMemcpyDeviceToHost, s));
+  GPRY_CUDA(cudaMemcpyAsync(prm.data(), st->prm_dev.p, 3 * MAX_DIM * 8, cudaMemcpyDeviceToHost, s));
+  GPRY_CUDA(cudaStreamSynchronize(s));
+  std::vector<double> lo(d, 1e300), hi(d, -1e300);
+  for (int j = 0; j < N; j++)
+    for (int k = 0; k < d; k++) {
+      lo[k] = std::min(lo[k], Xt[(size_t)j * d + k]);
+      hi[k] = std::max(hi[k], Xt[(size_t)j * d + k]);
+    }
+  uint64_t lcg = 0x9E3779B97F4A7C15ull;
+  for (int i = 0; i < P; i++)
+    for (int k = 0; k < d; k++) {
+      double xt;
+      if (i < P / 2) {
+        xt = Xt[(size_t)((int64_t)i * N / (P / 2)) * d + k];
+      } else {
+        lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+        xt = lo[k] + (hi[k] - lo[k]) * ((double)(lcg >> 11) * (1.0 / 9007199254740992.0));
+      }
+      probe[(size_t)i * d + k] = xt * prm[MAX_DIM + k] + prm[k];     // un-transform
+    }
+  st->oz_probe.reserve((size_t)P * d + 2 * (size_t)P);
+  double* dP = st->oz_probe.p;
+  double* sd8 = dP + (size_t)P * d;
+  double* sd64 = sd8 + P;
+  GPRY_CUDA(cudaMemcpyAsync(dP, probe.data(), (size_t)P * d * 8, cudaMemcpyHostToDevice, s));
+  const bool sel_on = st->sel.on;
+  const bool prof = st->profiling;
+  const int mode = st->contract_mode;
+  const double nl = st->n_launches, ncl = st->n_contract_launches;
+  st->sel.on = false;
+  st->profiling = false;
+  try {
+    predict_pipeline(st, dP, P, false, true, false, 0, 0, 0, nullptr, sd8, nullptr, s);
+    st->contract_mode = GPRY_CONTRACT_FP64;
+    predict_pipeline(st, dP, P, false, true, false, 0, 0, 0, nullptr, sd64, nullptr, s);
+  } catch (...) {
+    st->contract_mode = mode; st->sel.on = sel_on; st->profiling = prof;
+    throw;
+  }
+  st->contract_mode = mode;
+  st->sel.on = sel_on;
+  st->profiling = prof;
+  st->n_launches = nl;
+  st->n_contract_launches = ncl;
+  std::vector<double> h(2 * (size_t)P);
+  GPRY_CUDA(cudaMemcpyAsync(h.data(), sd8, 2 * (size_t)P * 8, cudaMemcpyDeviceToHost, s));
+  GPRY_CUDA(cudaStreamSynchronize(s));
+  double err = 0.0;
+  for (int i = 0; i < P; i++) {
+    const double a = h[i] / st->y_std, b = h[P + i] / st->y_std;
+    if (!(a == a) || !(b == b)) continue;
+    err = std::max(err, fabs(a * a - b * b) / std::max(b * b, 1.0));
+  }
+  st->oz_probe_err = err;
+  st->oz_ok = err * 16.0 <= OZ_TOLERANCE;
 }
 
 void mean_grad_device(gpry_state* st, const double* x_host, double* out_host) {

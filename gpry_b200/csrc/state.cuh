@@ -86,7 +86,12 @@ struct gpry_state {
   // INT8 split of the variance contraction (ozaki.cu); contract_mode: 0 = FP64 DMMA, 1 = INT8
   int contract_mode = 1;
   bool oz_valid = false;                 // digits of V / row scales / split lists are current
+  // guard of the INT8 split (ozaki.cu error model + probe comparison with the FP64 kernel):
+  // a model whose estimated or probed error exceeds the tolerance takes the FP64 contraction
+  bool oz_guard = true, oz_checked = false, oz_ok = true;
+  double oz_bound_worst = 0.0, oz_est_sigma = 0.0, oz_probe_err = -1.0;
   int oz_splits = 1, oz_max_rb = 0, oz_rows = 0;
+  gpry::DevBuf<double> oz_probe;         // probe candidates + their std from both kernels
   gpry::DevBuf<double> oz_park;          // per-SM scratch of the two-pass kernel (L2 resident)
   gpry::DevBuf<uint8_t> oz_Ksl, oz_Vs;   // digits of the K* chunk / of V
   gpry::DevBuf<double> oz_scale;         // [Npad] c 2^e_j 2^-12, then [Npad] 2^e_j
@@ -129,6 +134,12 @@ struct gpry_state {
   gpry::SelectRun sel;                   // host side of the selection in flight
   gpry::DevBuf<int64_t> excl;            // sorted local row numbers skipped by the ranking
   int n_excl = 0;
+  // NCCL communicator owned by the library (comm.cu) + exchange buffers
+  void* comm = nullptr;
+  bool comm_owner = true;
+  int comm_rank = 0, comm_size = 1;
+  gpry::DevBuf<double> cm_hdr, cm_send, cm_recv, mg_keys;
+  gpry::DevBuf<int64_t> mg_idx;
   gpry::DevBuf<double> tmp;              // upload staging (raw V etc.)
   gpry::DevBuf<double> small;            // small outputs (gradient, top-k records)
 
@@ -189,6 +200,19 @@ void std_grad_device(gpry_state* st, const double* x_host, double* out_grad, dou
 void select_begin(gpry_state* st, int Kp, int chunk_cands, cudaStream_t s);
 void select_compact(gpry_state* st, cudaStream_t s);
 int64_t select_finish(gpry_state* st, cudaStream_t s);
+void merge_records(gpry_state* st, const double* rec, int n, int R, int Kq, double** keys,
+                   int64_t** gidx, int** pos, cudaStream_t s);
+// comm.cu
+void comm_unique_id(void* out128);
+void comm_init(gpry_state* st, const void* id128, int rank, int nranks);
+void comm_destroy(gpry_state* st);
+void comm_share(gpry_state* dst, gpry_state* src);
+int comm_nccl_version();
+void bcast_state(gpry_state* st, int root, cudaStream_t s);
+void allgather_topk(gpry_state* st, int n_local, int Kp, int d, const double* acq,
+                    const int64_t* idx, const double* mean, const double* sd, const double* X,
+                    bool in_dev, bool out_dev, double* o_acq, int64_t* o_idx, double* o_mean,
+                    double* o_sd, double* o_X, int64_t* n_out, double* next_acq, cudaStream_t s);
 void gather_rows(gpry_state* st, const int64_t* d_idx, int64_t n, int64_t idx_base,
                  const double* dX, int d, double* o_X, cudaStream_t s);
 int64_t topk_device(gpry_state* st, const double* d_scores, int64_t M, int Kp, int64_t idx_base,
@@ -204,6 +228,8 @@ void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_tr
                       double* out_L, double* out_V, double* out_alpha, double* out_logdet_half,
                       int* info, bool keep);
 bool ozaki_supported(const gpry_state* st);
+void ozaki_validate(gpry_state* st, cudaStream_t s);
+constexpr double OZ_TOLERANCE = 1e-10;   // on the variance, in units of max(var, y_std^2)
 double ozaki_int8_peak_tops(gpry_state* st);
 void ozaki_prepare(gpry_state* st, cudaStream_t s);
 size_t ozaki_kslices_bytes(const gpry_state* st, int tiles);

@@ -284,6 +284,56 @@ int64_t select_finish(gpry_state* st, cudaStream_t s) {
   return (int64_t)h[0];
 }
 
+// ---------------------------------------------------------------------------------------
+// merge of all-gathered survivor records (comm.cu): rows of R doubles whose first two entries are
+// (acq, index as int64 bits) -> the Kq best, as sorted (key, index, row number) triples
+// ---------------------------------------------------------------------------------------
+__global__ void split_records_kernel(const double* __restrict__ rec, int n, int R,
+                                     double* __restrict__ keys, int64_t* __restrict__ gidx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = rec[(size_t)i * R];
+  gidx[i] = __double_as_longlong(rec[(size_t)i * R + 1]);
+}
+
+void merge_records(gpry_state* st, const double* rec, int n, int R, int Kq, double** keys,
+                   int64_t** gidx, int** pos, cudaStream_t s) {
+  GPRY_CHECK_ARG(Kq >= 1 && Kq <= TK_E, "merge: too many records requested");
+  st->mg_keys.reserve((size_t)n);
+  st->mg_idx.reserve((size_t)n);
+  split_records_kernel<<<(n + 255) / 256, 256, 0, s>>>(rec, n, R, st->mg_keys.p, st->mg_idx.p);
+  GPRY_CUDA(cudaGetLastError());
+  int64_t m = n;
+  int64_t nblocks = (m + TK_E - 1) / TK_E;
+  for (int b = 0; b < 2; b++) {
+    st->tk_keys[b].reserve((size_t)nblocks * Kq);
+    st->tk_idx[b].reserve((size_t)nblocks * Kq);
+    st->tk_pos[b].reserve((size_t)nblocks * Kq);
+  }
+  const size_t smem = (size_t)TK_E * 20;
+  GPRY_CUDA(cudaFuncSetAttribute(topk_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  const double* kin = st->mg_keys.p;
+  const int64_t* iin = st->mg_idx.p;
+  const int* pin = nullptr;
+  int lvl = 0;
+  while (true) {
+    nblocks = (m + TK_E - 1) / TK_E;
+    topk_rec_kernel<<<(unsigned)nblocks, TK_THREADS, smem, s>>>(
+        kin, iin, pin, nullptr, m, Kq, st->tk_keys[lvl].p, st->tk_idx[lvl].p, st->tk_pos[lvl].p);
+    GPRY_CUDA(cudaGetLastError());
+    kin = st->tk_keys[lvl].p;
+    iin = st->tk_idx[lvl].p;
+    pin = st->tk_pos[lvl].p;
+    if (nblocks == 1) break;
+    m = nblocks * Kq;
+    lvl ^= 1;
+  }
+  *keys = st->tk_keys[lvl].p;
+  *gidx = st->tk_idx[lvl].p;
+  *pos = st->tk_pos[lvl].p;
+}
+
 __global__ void gather_rows_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t idx_base,
                                    const double* __restrict__ X, int d, double* __restrict__ o_X) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

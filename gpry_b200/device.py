@@ -94,10 +94,23 @@ class DeviceGP:
             float(y_std), float(clip_hi)))
         self.N, self.d, self.kind = self._f_N, d, self._f_kind
 
-    def set_contract_mode(self, mode):
-        """"int8" (exact 7-digit integer split on the INT8 tensor cores, default) or "fp64"
-        (DMMA) for the variance contraction of large pools."""
+    def set_contract_mode(self, mode, guard=True):
+        """"int8" (Ozaki split into 7 int8 digits on the INT8 tensor cores, FP64-equivalent;
+        default) or "fp64" (DMMA) for the variance contraction of large pools.  With the guard
+        on (default) a model whose estimated or probed INT8 error exceeds the tolerance takes
+        the FP64 kernel anyway (see ``contract_info``)."""
         check(self._lib.gpry_set_contract_mode(self._h, {"fp64": 0, "int8": 1, "int8_1pass": 2}[mode]))
+        check(self._lib.gpry_set_contract_guard(self._h, 1 if guard else 0))
+
+    def contract_info(self):
+        """What the INT8 guard decided for the uploaded model."""
+        out = np.zeros(8)
+        check(self._lib.gpry_contract_info(self._h, ptr(out)))
+        names = {0: "fp64", 1: "int8", 2: "int8_1pass"}
+        return {"requested": names[int(out[0])], "in_use": names[int(out[1])],
+                "estimate_sigma": out[2], "bound_worst_case": out[3],
+                "probe_diff": None if out[4] < 0 else out[4], "tolerance": out[5],
+                "guard": bool(out[6])}
 
     def int8_peak_tops(self):
         """Measured tcgen05 INT8 MMA issue rate of this GPU (TOPS): roofline denominator."""
@@ -370,6 +383,54 @@ class DeviceGP:
             self._h, KERNEL_KINDS[kind], N, d, ptr(X_train_), ptr(noise2), ptr(y_train_),
             ptr(thetas), B, ptr(lml), ptr(grad), ptr(info)))
         return lml, grad, info
+
+    # ------------------------------------------------------------------ multi-GPU exchange
+    def comm_unique_id(self):
+        """128-byte NCCL id (create on rank 0, ship to the others over any host channel)."""
+        buf = C.create_string_buffer(128)
+        check(self._lib.gpry_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid, rank, nranks):
+        check(self._lib.gpry_comm_init(self._h, C.c_char_p(uid), int(rank), int(nranks)))
+
+    def comm_share(self, other):
+        """Use ``other``'s communicator (same process, same GPU)."""
+        check(self._lib.gpry_comm_share(self._h, other._h))
+
+    def comm_info(self):
+        r, n, v = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(self._lib.gpry_comm_info(self._h, C.byref(r), C.byref(n), C.byref(v)))
+        return {"rank": r.value, "size": n.value, "nccl_version": v.value}
+
+    def bcast_state(self, root=0, stream=None):
+        """The model uploaded on ``root`` -> this state on every rank, GPU to GPU (NCCL)."""
+        check(self._lib.gpry_bcast_state(self._h, int(root), _stream_ptr(stream)))
+        info = [C.c_int(0), C.c_int(0), C.c_int(0)]
+        check(self._lib.gpry_state_info(self._h, *[C.byref(i) for i in info]))
+        self.N, self.d = info[0].value, info[1].value
+        self.kind = {v: k for k, v in KERNEL_KINDS.items()}[info[2].value]
+
+    def allgather_topk(self, acq, idx, mean, std, X, Kp, d=None, stream=None):
+        """Every rank's survivor records -> the Kp best of the union (numpy arrays, the same on
+        every rank) and the best acquisition value left out: (acq, idx, mean, std, X, next)."""
+        n = len(acq)
+        on_dev = _is_torch_cuda(acq)
+        d = (X.shape[1] if X is not None else 0) if d is None else d
+        if not on_dev:
+            acq, mean, std = as_f64(acq), as_f64(mean), as_f64(std)
+            idx = np.ascontiguousarray(idx, dtype=np.int64)
+            X = as_f64(X)
+        Kp = int(Kp)
+        o_acq, o_mean, o_std = np.empty(Kp), np.empty(Kp), np.empty(Kp)
+        o_idx, o_X = np.empty(Kp, dtype=np.int64), np.empty((Kp, d))
+        n_out, nxt = C.c_int64(0), C.c_double(0.0)
+        check(self._lib.gpry_allgather_topk(
+            self._h, n, Kp, d, ptr(acq), ptr(idx), ptr(mean), ptr(std), ptr(X),
+            _lib.X_ON_DEVICE if on_dev else 0, ptr(o_acq), ptr(o_idx), ptr(o_mean), ptr(o_std),
+            ptr(o_X), C.byref(n_out), C.byref(nxt), _stream_ptr(stream)))
+        k = n_out.value
+        return o_acq[:k], o_idx[:k], o_mean[:k], o_std[:k], o_X[:k], nxt.value
 
     # ------------------------------------------------------------------ profiling
     def set_profiling(self, enable=True):

@@ -406,15 +406,11 @@ class NORA:
                                   np.empty(0), np.empty((0, gpr.d)))
             local_cut = float(a[-1]) if (n_live > Kp_eff and len(a)) else -np.inf
             i = i * size + rank       # position in the un-sharded sample
-            a, i, m, s, Xs = parallel.allgather_survivors(a, i, m, s, Xs)
-            order = np.lexsort((i, -a))
-            if len(order) > Kp_eff:
-                # Only the best K' of the union are ranked (keeps the posterior covariance at
-                # K' x K' whatever the number of ranks); the first row left out bounds what
-                # any dropped row could have scored, like a shard's own cut
-                local_cut = max(local_cut, float(a[order[Kp_eff]]))
-                order = order[:Kp_eff]
-            a, i, m, s, Xs = a[order], i[order], m[order], s[order], Xs[order]
+            # Only the best K' of the union are ranked (keeps the posterior covariance at
+            # K' x K' whatever the number of ranks); the first row left out bounds what any
+            # dropped row could have scored, like a shard's own cut
+            a, i, m, s, Xs, dropped = parallel.merge_survivors(a, i, m, s, Xs, Kp_eff)
+            local_cut = max(local_cut, dropped)
             pool = ranked_pool_from_scores(gpr, Xs, m, s, a, n_points, acq_func)
             # Exactness of the pre-selection (module docstring): every candidate that was NOT
             # ranked has acq <= cut; if cut <= the last-slot conditioned acq of a full pool,

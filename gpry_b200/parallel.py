@@ -202,6 +202,42 @@ def allgather_survivors(acq, idx, mean, std, X):
             allrec[:, 3].copy(), np.ascontiguousarray(allrec[:, 4:]))
 
 
+_device_comm = {}
+
+
+def device_comm(device=None):
+    """The process-wide ``DeviceGP`` of this rank's GPU with the library's own NCCL communicator
+    over the whole process group (created on first use: rank 0 makes the 128-byte id, it travels
+    through ``bcast``), or None when the ranks do not each own a GPU (gloo / serial runs)."""
+    if not (_on() and multiple_processes() and dist.get_backend() == "nccl"):
+        return None
+    from .device import workspace
+    device = torch.cuda.current_device() if device is None else device
+    if device not in _device_comm:
+        ws = workspace(device)
+        uid = bcast(ws.comm_unique_id() if is_main_process() else None)
+        ws.comm_init(uid, rank(), size())
+        _device_comm[device] = ws
+    return _device_comm[device]
+
+
+def merge_survivors(acq, idx, mean, std, X, Kp):
+    """Exchange step of the ranked pool: every rank's (at most Kp) survivor records -> the Kp
+    best of the union in visiting order (descending acq, ascending global index), identical on
+    every rank, plus the best acquisition value that was left out (-inf if nothing was).
+    One ``ncclAllGather`` + device merge inside the library (``gpry_allgather_topk``) when every
+    rank owns a GPU; tensor collectives of ``torch.distributed`` otherwise (gloo, CPU tests).
+    Replaces gp_acquisition.py:1148-1171 + bcast :1190."""
+    ws = device_comm()
+    if ws is not None:
+        return ws.allgather_topk(acq, idx, mean, std, X, Kp, d=X.shape[1])
+    acq, idx, mean, std, X = allgather_survivors(acq, idx, mean, std, X)
+    order = np.lexsort((idx, -acq))
+    nxt = float(acq[order[Kp]]) if len(order) > Kp else -np.inf
+    order = order[:Kp]
+    return acq[order], idx[order], mean[order], std[order], X[order], nxt
+
+
 def best_fit_across_processes(lml, theta):
     """run.py:1286-1293: all-gather (lml, theta) of every rank's best restart; every rank
     returns the global best (ties -> lowest rank), so no pickled regressor has to travel: the

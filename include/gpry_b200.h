@@ -113,18 +113,33 @@ int gpry_set_trust_region(gpry_state* st, int d, const double* lower, const doub
 /*
  * How the variance contraction sum_j (sum_k V_jk k*_ik)^2 of gpr.py:1204-1208 is evaluated:
  *   GPRY_CONTRACT_FP64            FP64 tensor cores (DMMA.8x8x4)
- *   GPRY_CONTRACT_INT8 (default)  exact integer split of both operands into 7 int8 digits, 28
- *                                 digit products on the INT8 tensor cores (tcgen05.mma kind::i8,
- *                                 int32 accumulators in TMEM), recombined in FP64; same result
- *                                 to within the rounding error of an FP64 dot product.  Used for
- *                                 512 <= N_pad <= 16384 and more than 64 candidates per call;
- *                                 other calls use FP64.  The environment variable
- *                                 GPRY_B200_CONTRACT=fp64|int8|int8_1pass sets the initial mode of new states.
+ *   GPRY_CONTRACT_INT8 (default)  Ozaki split: both operands rounded to 55-bit fixed point
+ *                                 (k* / c to 2^-54, V_jk to 2^(e_j - 54), e_j the exponent of the
+ *                                 row maximum) and written as 7 balanced int8 digits; the 28 digit
+ *                                 products of groups p + q <= 6 run on the INT8 tensor cores
+ *                                 (tcgen05.mma kind::i8, exact int32 accumulators in TMEM) and are
+ *                                 recombined in FP64.  FP64-EQUIVALENT, not exact: per row product
+ *                                 the error is <= 7.02 c 2^e_j n_j 2^-54 in the worst case and
+ *                                 ~2.2 c 2^-55 sqrt((|V_j|^2 + 4^e_j n_j) / 3) statistically
+ *                                 (n_j = j + 1 terms); d var <= 2 sqrt(c) max_j |d w_j|.
+ *                                 Eligible: 512 <= N_pad <= 16384 and more than 64 candidates per
+ *                                 call; other calls use FP64.
+ * GUARD (on by default): once per uploaded model the statistical estimate is evaluated and 512
+ * probe candidates (training points + draws from their bounding box) are scored with BOTH
+ * kernels; if the estimate exceeds 1e-10 or the probes differ by more than 1e-10 / 16 (variance,
+ * in units of max(var, y_std^2)) the model takes the FP64 kernel.  gpry_contract_info reports
+ * what was decided: out8 = [mode requested, mode in use, statistical estimate, worst-case bound,
+ * probe difference (-1: not probed), tolerance, guard on, 0].  gpry_set_contract_guard(st, 0)
+ * switches the guard off (measurements of the raw INT8 path).
+ * The environment variable GPRY_B200_CONTRACT=fp64|int8|int8_1pass sets the initial mode of new
+ * states.
  */
 #define GPRY_CONTRACT_FP64 0
 #define GPRY_CONTRACT_INT8 1       /* two passes over the digit groups, 128 x 128 x 32 MMAs */
 #define GPRY_CONTRACT_INT8_1PASS 2 /* one pass, 128 x 64 x 32 MMAs (all 7 groups in TMEM at once) */
 int gpry_set_contract_mode(gpry_state* st, int mode);
+int gpry_set_contract_guard(gpry_state* st, int enable);
+int gpry_contract_info(gpry_state* st, double* out8);
 
 /* Measured issue rate (TOPS, 2 ops per multiply-add) of tcgen05.mma kind::i8 at its best shape
  * (128 x 256 x 32) on operands resident in shared memory, all SMs busy: the roofline
@@ -272,6 +287,45 @@ int gpry_factor_download(gpry_state* st, double* out_L, double* out_V);
 int gpry_lml_batched(gpry_state* st, int kind, int N, int d, const double* X_train_t,
                      const double* noise2, const double* y_t, const double* thetas, int B,
                      double* out_lml, double* out_grad, int* out_info);
+
+/*
+ * Multi-GPU exchange steps on an NCCL communicator owned by the library (one process per GPU;
+ * NCCL is bound at run time with dlopen("libnccl.so.2"), so a process that imported PyTorch
+ * shares PyTorch's copy).  They replace the reference's mpi4py traffic for this path:
+ *
+ *   gpry_comm_unique_id   rank 0 creates the 128-byte NCCL id; ship it to the other ranks by any
+ *                         host channel (the reference's own MPI.COMM_WORLD.bcast, mpi.py:53-59, or
+ *                         torch.distributed) ...
+ *   gpry_comm_init        ... and every rank joins with (id, rank, nranks) on its state's GPU.
+ *   gpry_bcast_state      the model uploaded into `root`'s state (X_train_, alpha_, V_ = L^-1,
+ *                         kernel and pre-processor scalars) goes GPU -> GPU over NVLink into every
+ *                         other rank's state, which is then ready for gpry_predict*: what the
+ *                         scoring ranks need of the pickled regressor that run.py:749-756
+ *                         (_share_gpr -> mpi.bcast) ships once per refit.  The device-side
+ *                         classifier and trust region are not part of it (set them per rank).
+ *   gpry_allgather_topk   every rank contributes n_local <= Kp survivor records (acq, idx, mean,
+ *                         std, X[d]; host or device per GPRY_X_ON_DEVICE) and receives the Kp best
+ *                         of the union, sorted by (descending acq, ascending idx), identical on
+ *                         all ranks: gp_acquisition.py:1148-1171 (_gather_pools, five gathers) and
+ *                         the bcast of :1190 in one ncclAllGather + a device merge.  *n_out =
+ *                         records returned; *next_acq = the best acquisition value NOT returned
+ *                         (-inf if none): the bound NORA's exact pre-selection test needs.
+ *                         mean / std / X (and their outputs) may be NULL.
+ */
+int gpry_comm_unique_id(void* out128);
+int gpry_comm_init(gpry_state* st, const void* id128, int rank, int nranks);
+/* dst borrows src's communicator (same process and GPU; src must outlive its use): lets every
+ * model state of a process use one communicator. */
+int gpry_comm_share(gpry_state* dst, gpry_state* src);
+int gpry_comm_destroy(gpry_state* st);
+/* rank, size (0 = no communicator) and the NCCL version bound (e.g. 22809); any may be NULL */
+int gpry_comm_info(const gpry_state* st, int* rank, int* nranks, int* nccl_version);
+int gpry_bcast_state(gpry_state* st, int root, void* stream);
+int gpry_allgather_topk(gpry_state* st, int n_local, int Kp, int d, const double* acq,
+                        const int64_t* idx, const double* mean, const double* std_,
+                        const double* X, int where, double* out_acq, int64_t* out_idx,
+                        double* out_mean, double* out_std, double* out_X, int64_t* n_out,
+                        double* next_acq, void* stream);
 
 /* Device timings (ms, CUDA events on the launching stream) accumulated since the last
  * reset, per stage: [0] kstar build, [1] variance contraction, [2] finish/acquisition,

@@ -93,7 +93,7 @@ def test_int8_nonfinite_and_extreme_scales(dev):
     Xc[11, 0] = np.inf
     res = {}
     for mode in ("fp64", "int8"):
-        dev.set_contract_mode(mode)
+        dev.set_contract_mode(mode, guard=False)      # the raw integer path, whatever the guard says
         res[mode] = dev.predict_logexp(Xc, 0.3, st.noise_level, st.y_max)
     dev.set_contract_mode("int8")
     m8, s8, a8 = res["int8"]
@@ -109,6 +109,51 @@ def test_int8_nonfinite_and_extreme_scales(dev):
     err64 = np.max(np.abs(s64[good][:600] ** 2 - so ** 2)) / (c * st.y_std ** 2)
     err8 = np.max(np.abs(s8[good][:600] ** 2 - so ** 2)) / (c * st.y_std ** 2)
     assert err8 < max(1e-10, 4 * err64)
+
+
+def test_guard_headline_model_stays_int8(dev):
+    """N_train = 2000, d = 12, c = 1 (the benchmark's model): estimate and probe are far below
+    the tolerance, the INT8 kernel is used."""
+    X, y, theta, bounds = orc.synthetic_problem(2000, 12)
+    st = orc.GPState("rbf", theta, X, y, bounds=bounds)
+    upload_from_oracle(dev, st)
+    dev.set_contract_mode("int8")
+    info = dev.contract_info()
+    assert info["requested"] == "int8" and info["in_use"] == "int8" and info["guard"]
+    assert info["estimate_sigma"] < info["tolerance"] < info["bound_worst_case"]
+    assert info["probe_diff"] is not None and info["probe_diff"] * 16 <= info["tolerance"]
+
+
+@pytest.mark.parametrize("c,ell,noise", [(1e6, 8.0, 1e-2), (1.0, 1e-3, 1e-2), (100.0, 1.0, 1e-2),
+                                         (1e4, 1.0, 1e-4)])
+def test_guard_falls_back_when_the_split_is_not_safe(dev, c, ell, noise):
+    """theta where GPry's own fits drift (c = 1e6, l ~ 8: SURVEY section 7), a vanishing length
+    scale, and large output scales: whatever the guard decides, the result must be as close to
+    the reference as the FP64 kernel's (or within 1e-10); where the estimate exceeds the
+    tolerance the FP64 kernel must be the one in use."""
+    N, d = 900, 6
+    X, y, theta, bounds = orc.synthetic_problem(N, d)
+    theta = np.log(np.concatenate([[c], np.full(d, ell)]))
+    try:
+        st = orc.GPState("rbf", theta, X, y, bounds=bounds, noise_level=noise)
+    except np.linalg.LinAlgError:
+        pytest.skip("not positive definite on the host either")
+    upload_from_oracle(dev, st)
+    Xc = np.concatenate([np.random.default_rng(5).uniform(size=(1500, d)), X[:300]])
+    mo, so = orc.predict(st, Xc, return_std=True)
+    dev.set_contract_mode("fp64")
+    _, s64 = dev.predict(Xc, return_std=True)
+    dev.set_contract_mode("int8")
+    info = dev.contract_info()
+    _, s8 = dev.predict(Xc, return_std=True)
+    scale = np.maximum(so ** 2, st.y_std ** 2)
+    err64 = np.max(np.abs(s64 ** 2 - so ** 2) / scale)
+    err8 = np.max(np.abs(s8 ** 2 - so ** 2) / scale)
+    assert err8 <= max(1e-10, 2 * err64), (info, err8, err64)
+    if info["estimate_sigma"] > info["tolerance"]:
+        assert info["in_use"] == "fp64" and np.array_equal(s8, s64)
+    if c >= 1e4:
+        assert info["in_use"] == "fp64"
 
 
 def test_int8_used_only_where_supported(dev):
