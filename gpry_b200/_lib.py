@@ -42,6 +42,7 @@ SIGNATURES = {
     "gpry_set_contract_guard": (C.c_int, [C.c_void_p, C.c_int]),
     "gpry_contract_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gpry_int8_peak": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gpry_int8_peak_sustained": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
     "gpry_set_mask_value": (C.c_int, [C.c_void_p, C.c_double]),
     "gpry_set_classifier": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_double, C.c_double]),

@@ -319,6 +319,14 @@ int gpry_int8_peak(gpry_state* st, double* out_tops) {
   });
 }
 
+int gpry_int8_peak_sustained(gpry_state* st, double seconds, double* out_tops) {
+  return guarded([&] {
+    GPRY_CHECK_ARG(st != nullptr && out_tops != nullptr, "NULL argument");
+    GPRY_CHECK_ARG(seconds > 0.0 && seconds <= 30.0, "seconds must be in (0, 30]");
+    *out_tops = ozaki_int8_peak_sustained_tops(st, seconds);
+  });
+}
+
 int gpry_set_mask_value(gpry_state* st, double value) {
   return guarded([&] {
     GPRY_CHECK_ARG(st != nullptr, "state is NULL");

@@ -546,6 +546,35 @@ double ozaki_int8_peak_tops(gpry_state* st) {
   return ops / (best * 1e-3) * 1e-12;
 }
 
+// The same kernel launched back to back for `seconds`: the rate the board sustains under its
+// power cap (what a kernel timed inside a long step can reach), measured over the last 3/4.
+double ozaki_int8_peak_sustained_tops(gpry_state* st, double seconds) {
+  GPRY_CUDA(cudaSetDevice(st->device));
+  const size_t smem = 4 * 4096 + 4 * 8192;
+  GPRY_CUDA(cudaFuncSetAttribute(oz_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  const int reps = 2000;                                   // ~10 ms per launch
+  const int n = std::max(8, (int)(seconds / 0.0095));
+  cudaEvent_t e0, e1;
+  GPRY_CUDA(cudaEventCreate(&e0));
+  GPRY_CUDA(cudaEventCreate(&e1));
+  int timed = 0;
+  for (int i = 0; i < n; i++) {
+    if (i == n / 4) GPRY_CUDA(cudaEventRecord(e0));
+    oz_peak_kernel<<<st->n_sm, 128, smem>>>(reps);
+    if (i >= n / 4) timed++;
+  }
+  GPRY_CUDA(cudaEventRecord(e1));
+  GPRY_CUDA(cudaEventSynchronize(e1));
+  GPRY_CUDA(cudaGetLastError());
+  float ms;
+  GPRY_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double ops = 2.0 * (double)st->n_sm * reps * 16 * 4 * 128.0 * 256.0 * 32.0 * timed;
+  return ops / (ms * 1e-3) * 1e-12;
+}
+
 bool ozaki_supported(const gpry_state* st) {
   if (!(st->has_V && st->Npad >= 512 && st->Npad <= 16384)) return false;
   // the guard (ozaki_prepare + ozaki_validate) has ruled the split out for this model

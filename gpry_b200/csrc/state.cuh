@@ -231,6 +231,7 @@ bool ozaki_supported(const gpry_state* st);
 void ozaki_validate(gpry_state* st, cudaStream_t s);
 constexpr double OZ_TOLERANCE = 1e-10;   // on the variance, in units of max(var, y_std^2)
 double ozaki_int8_peak_tops(gpry_state* st);
+double ozaki_int8_peak_sustained_tops(gpry_state* st, double seconds);
 void ozaki_prepare(gpry_state* st, cudaStream_t s);
 size_t ozaki_kslices_bytes(const gpry_state* st, int tiles);
 void ozaki_contract(gpry_state* st, const uint8_t* Ksl, int tiles, int chunk_cands, cudaStream_t s);

@@ -112,10 +112,15 @@ class DeviceGP:
                 "probe_diff": None if out[4] < 0 else out[4], "tolerance": out[5],
                 "guard": bool(out[6])}
 
-    def int8_peak_tops(self):
-        """Measured tcgen05 INT8 MMA issue rate of this GPU (TOPS): roofline denominator."""
+    def int8_peak_tops(self, seconds=None):
+        """Measured tcgen05 INT8 MMA issue rate of this GPU (TOPS): roofline denominator.  A 2 ms
+        burst by default; ``seconds``: launched back to back for that long (sustained under the
+        power cap)."""
         out = C.c_double(0.0)
-        check(self._lib.gpry_int8_peak(self._h, C.byref(out)))
+        if seconds is None:
+            check(self._lib.gpry_int8_peak(self._h, C.byref(out)))
+        else:
+            check(self._lib.gpry_int8_peak_sustained(self._h, float(seconds), C.byref(out)))
         return out.value
 
     def set_mask_value(self, value):

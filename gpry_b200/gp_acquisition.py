@@ -24,6 +24,7 @@ the reference step by step so that the resulting pool is the same.
 """
 from copy import deepcopy
 from functools import partial
+from time import perf_counter
 
 import numpy as np
 
@@ -300,7 +301,8 @@ class NORA:
         self.mc_every = mc_every
         self.mc_every_i = 0
         self.sampler = sampler
-        self.nsamples = nsamples if nsamples is not None else 1000 * d
+        self.nsamples = nsamples if nsamples is not None else 1000 * d      # (sampler=None: the
+        # caller always hands the MC sample in, through X_mc / X_shard)
         self.mc_steps = mc_steps
         self.kprime = kprime
         self.verbose = verbose
@@ -396,14 +398,17 @@ class NORA:
         skip = np.sort(done[done % size == rank] // size) if len(done) else None
         n_live = n_this - (0 if skip is None else len(skip))
         Kp = max(self.kprime, 4 * n_points)
+        timing = {"score_s": 0.0, "exchange_s": 0.0, "rank_s": 0.0}
         while True:
             Kp_eff = min(Kp, 2048)
+            t0 = perf_counter()
             if n_live > 0:
                 a, i, m, s, Xs = gpr.predict_logexp_topk(this_X, zeta, Kp_eff, exclude=skip)
                 a, i, m, s, Xs = (_to_numpy(v) for v in (a, i, m, s, Xs))
             else:
                 a, i, m, s, Xs = (np.empty(0), np.empty(0, dtype=np.int64), np.empty(0),
                                   np.empty(0), np.empty((0, gpr.d)))
+            t1 = perf_counter()
             local_cut = float(a[-1]) if (n_live > Kp_eff and len(a)) else -np.inf
             i = i * size + rank       # position in the un-sharded sample
             # Only the best K' of the union are ranked (keeps the posterior covariance at
@@ -411,7 +416,12 @@ class NORA:
             # dropped row could have scored, like a shard's own cut
             a, i, m, s, Xs, dropped = parallel.merge_survivors(a, i, m, s, Xs, Kp_eff)
             local_cut = max(local_cut, dropped)
+            t2 = perf_counter()
             pool = ranked_pool_from_scores(gpr, Xs, m, s, a, n_points, acq_func)
+            t3 = perf_counter()
+            timing["score_s"] += t1 - t0
+            timing["exchange_s"] += t2 - t1
+            timing["rank_s"] += t3 - t2
             # Exactness of the pre-selection (module docstring): every candidate that was NOT
             # ranked has acq <= cut; if cut <= the last-slot conditioned acq of a full pool,
             # none of them could have entered.
@@ -425,6 +435,7 @@ class NORA:
                 break
             Kp *= 2
         self.last_kprime = Kp_eff
+        self.last_timing = timing
         self.pool = pool
         merged = pool.copy(drop_empty=True)
         X_pool, y_pool = merged.X[:n_points], merged.y[:n_points]

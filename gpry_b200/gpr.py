@@ -619,6 +619,12 @@ class GaussianProcessRegressor:
         self._factor_resident = True
         self._dev_dirty = True
 
+    def drop_resident_factor(self):
+        """Forget the device-resident factorisation: the next ``_update_model`` factorises from
+        scratch instead of bordering the old factor."""
+        self._factor_resident = False
+        self._fact_sig = None
+
     # ------------------------------------------------------------------ device state
     def _device_state(self):
         """Uploads (lazily, once per model change) what predict needs."""

@@ -267,22 +267,36 @@ def fit_gpr_parallel(gpr, new_X, new_y, n_restarts=None, hyperparameter_bounds=N
     """
     n_total = gpr.n_restarts_optimizer if n_restarts is None else n_restarts
     mine = int(split_number_for_parallel_processes(n_total)[rank()])
-    if mine or is_main_process():
-        gpr.append_to_data(
-            new_X, new_y, fit_classifier=True,
-            fit_gpr=({"n_restarts": mine, "start_from_current": is_main_process(),
-                      "hyperparameter_bounds": hyperparameter_bounds} if mine else False))
-        lml = gpr.log_marginal_likelihood_value_ if mine else -np.inf
-    else:   # no run assigned: still add the points (kept-constant hyper-parameters)
-        gpr.append_to_data(new_X, new_y, fit_classifier=True, fit_gpr=False)
-        lml = -np.inf
+    # Distinct restart points per rank (run.py:1243-1248 hands every rank its own child
+    # generator, mpi.py:31-50): with one shared integer seed every rank would draw the SAME
+    # starts and the split would only duplicate work.
+    seed = gpr.random_state
+    if multiple_processes() and not isinstance(seed, np.random.Generator):
+        gpr.random_state = get_random_generator(
+            seed if isinstance(seed, (int, np.integer)) or seed is None else None)
+    try:
+        if mine or is_main_process():
+            gpr.append_to_data(
+                new_X, new_y, fit_classifier=True,
+                fit_gpr=({"n_restarts": mine, "start_from_current": is_main_process(),
+                          "hyperparameter_bounds": hyperparameter_bounds} if mine else False))
+            lml = gpr.log_marginal_likelihood_value_ if mine else -np.inf
+        else:   # no run assigned: still add the points (kept-constant hyper-parameters)
+            gpr.append_to_data(new_X, new_y, fit_classifier=True, fit_gpr=False)
+            lml = -np.inf
+    finally:
+        gpr.random_state = seed
     theta = gpr.kernel_.theta
     best_lml, best_theta, best_rank = best_fit_across_processes(lml, theta)
     if multiple_processes() and np.isfinite(best_lml):
-        if not np.array_equal(best_theta, theta):
-            gpr.kernel_.theta = best_theta
-            gpr.newly_appended_for_inv = max(gpr.newly_appended_for_inv, 1)
-            gpr._update_model()
+        # Every rank factorises the winning theta from scratch -- also the winner, and also a
+        # rank whose theta already equals it: a bordered append or a factor computed before the
+        # exchange could differ from a fresh one in the last bits, and rank-replicated decisions
+        # taken later (ties in the ranking) must see identical numbers everywhere.
+        gpr.kernel_.theta = best_theta
+        gpr.newly_appended_for_inv = max(gpr.newly_appended_for_inv, 1)
+        gpr.drop_resident_factor()
+        gpr._update_model()
         gpr.log_marginal_likelihood_value_ = best_lml
         gpr._fitted = True
     return best_rank

@@ -145,6 +145,9 @@ int gpry_contract_info(gpry_state* st, double* out8);
  * (128 x 256 x 32) on operands resident in shared memory, all SMs busy: the roofline
  * denominator of the INT8 contraction.  Takes a few milliseconds. */
 int gpry_int8_peak(gpry_state* st, double* out_tops);
+/* The same measurement launched back to back for `seconds` (<= 30): the rate sustained under the
+ * board's power cap, i.e. the denominator for a kernel timed inside a long step. */
+int gpry_int8_peak_sustained(gpry_state* st, double seconds, double* out_tops);
 
 /* The value written by the two masks (GaussianProcessRegressor.minus_inf_value, read at call
  * time by the reference: gpr.py:1145, 1201; gp_acquisition.py:788-792 changes it temporarily). */

@@ -55,6 +55,44 @@ def _worker(rank, world, port, out_dir):
     nora = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=128)
     X_pool, y_pool, acq_pool = nora.multi_add(gpr2, n_points=int(g["pool_n_points"]), X_mc=Xp)
     assert np.array_equal(X_pool, Xp[g["pool_idx_single_sort_acq"]])
+    # every rank hands in only its rows; the exchange is gpry_allgather_topk (NCCL inside the
+    # library); second call on the same shards skips what the first proposed
+    comm = parallel.device_comm()
+    assert comm is not None and comm.comm_info()["size"] == world
+    shard = np.ascontiguousarray(Xp[rank::world])
+    nora2 = NORA(g["bounds"], acq_func=LogExp(zeta=g["zeta"]), kprime=128)
+    Xs1, _, _ = nora2.multi_add(gpr2, n_points=int(g["pool_n_points"]), X_shard=shard)
+    assert np.array_equal(nora2.last_pool_idx, g["pool_idx_single_sort_acq"])
+    Xs2, _, _ = nora2.multi_add(gpr2, n_points=int(g["pool_n_points"]), X_shard=shard)
+    assert not set(map(bytes, Xs2)) & set(map(bytes, Xs1))
+    # --- gpry_allgather_topk against the tensor-collective + numpy merge
+    rng = np.random.default_rng(7 + rank)
+    n_loc, Kq, dd = 50 + 13 * rank, 64, 3
+    a = np.sort(rng.normal(size=n_loc))[::-1].copy()
+    a[-3:] = -np.inf
+    i = (np.arange(n_loc) * world + rank).astype(np.int64)
+    m, s_, Xr = rng.normal(size=n_loc), rng.uniform(size=n_loc), rng.uniform(size=(n_loc, dd))
+    got = comm.allgather_topk(a, i, m, s_, Xr, Kq)
+    ua, ui, um, us, uX = parallel.allgather_survivors(a, i, m, s_, Xr)
+    order = np.lexsort((ui, -ua))
+    assert np.array_equal(got[1], ui[order[:Kq]]) and np.array_equal(got[0], ua[order[:Kq]])
+    assert np.array_equal(got[2], um[order[:Kq]]) and np.array_equal(got[3], us[order[:Kq]])
+    assert np.array_equal(got[4], uX[order[:Kq]]) and got[5] == ua[order[Kq]]
+    # --- gpry_bcast_state: rank 0's model -> a fresh state on the other GPU, same predictions
+    from gpry_b200 import DeviceGP
+    probe = DeviceGP(rank)
+    probe.comm_share(comm)
+    src = gpr2._device_state()
+    if rank == 0:
+        src.comm_share(comm)
+        src.bcast_state(0)
+    else:
+        probe.bcast_state(0)
+    Xq = g["Xc"]
+    mine = (src if rank == 0 else probe).predict(Xq, return_std=True)
+    both = parallel.allgather(mine)
+    assert np.array_equal(both[0][0], both[1][0]) and np.array_equal(both[0][1], both[1][1])
+    probe.close()
     # --- BatchOptimizer: restarts split over the ranks, every rank returns the same batch
     from gpry_b200.gp_acquisition import BatchOptimizer
     opt = BatchOptimizer(g["bounds"], preprocessing_X=Normalize_bounds(g["bounds"]),
