@@ -208,22 +208,40 @@ constexpr int OZ2_STAGE_BYTES = OZ_NS * (OZ_A_BYTES + OZ2_B_BYTES);  // 57344
 constexpr int OZ2_STAGES = 4;                                        // 224 KB
 constexpr size_t OZ2_SMEM = (size_t)OZ2_STAGES * OZ2_STAGE_BYTES + 256;
 constexpr int OZ2_PARK_SLOTS = 256;                                  // indexed by %smid
-constexpr uint32_t OZ2_IDESC = (2u << 4) | (1u << 7) | (1u << 10) |
-                               ((uint32_t)(OZ2_ROWS >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
 
-__device__ __forceinline__ void oz2_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+// idesc of a 128 x n x 32 MMA (n a multiple of 16)
+__device__ __forceinline__ constexpr uint32_t oz2_idesc(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(TILE_ROWS >> 4) << 24);
+}
+__device__ __forceinline__ void oz2_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                        uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(OZ2_IDESC), "r"(accumulate), "r"(0u)
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
+}
+// Structural zeros of the lower-triangular V inside a 128-row block rb (k chunks of 32):
+//  * chunk kc = 4 rb + q (q = 0..3, the diagonal 128 x 128 block): rows below 32 q are zero in
+//    this chunk, so the MMA covers rows 32 q .. only (N = rows_blk - 32 q, operand and
+//    accumulator start shifted by 32 q rows / columns);
+//  * the last row block holds rows_blk = round_up(N_train - 128 rb, 16) <= 128 real rows: the
+//    MMAs stop there and its diagonal chunks with 32 q >= rows_blk do not exist.
+__device__ __forceinline__ int oz2_rows_blk(int rb, int n_train) {
+  const int left = n_train - rb * OZ2_ROWS;
+  return left >= OZ2_ROWS ? OZ2_ROWS : ((left + 15) & ~15);
+}
+__device__ __forceinline__ int oz2_nch(int rb, int rows_blk) {
+  return 4 * rb + ((rows_blk + 31) >> 5);
 }
 
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__ Vs, int nKC,
                     const double* __restrict__ row_scale, const int* __restrict__ rb_list,
                     const int* __restrict__ rb_count, int max_rb, double* __restrict__ park,
-                    double* __restrict__ ssqp, int chunk_cands, int n_splits, int n_tiles) {
+                    double* __restrict__ ssqp, int chunk_cands, int n_splits, int n_tiles,
+                    int n_train) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)OZ2_STAGES * OZ2_STAGE_BYTES);
   uint64_t* empty = full + OZ2_STAGES;
@@ -265,7 +283,7 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
       for (int r = 0; r < n_rb; r++) {
         const int rb = my_rb[r];
         const uint8_t* Bbase = Vs + (size_t)rb * nKC * (size_t)(OZ_NS * OZ2_B_BYTES);
-        const int nch = 4 * (rb + 1);      // rows 128 rb .. +127 are zero beyond k = 128 (rb + 1)
+        const int nch = oz2_nch(rb, oz2_rows_blk(rb, n_train));   // no k beyond the block's last row
         for (int pass = 0; pass < 2; pass++) {
           const uint32_t nd = pass == 0 ? 4u : (uint32_t)OZ_NS;      // digits of each operand needed
           for (int kc = 0; kc < nch; kc++, it++) {
@@ -289,7 +307,9 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
       const int n_rb = rb_count[split];
       const int* my_rb = rb_list + (size_t)split * max_rb;
       for (int r = 0; r < n_rb; r++) {
-        const int nch = 4 * (my_rb[r] + 1);
+        const int rb = my_rb[r];
+        const int rows_blk = oz2_rows_blk(rb, n_train);
+        const int nch = oz2_nch(rb, rows_blk);
         for (int pass = 0; pass < 2; pass++, t++) {
           oz_wait(tmem_empty, (t & 1) ^ 1);        // the previous epilogue has drained TMEM
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -298,24 +318,28 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
             oz_wait(&full[s], (it / OZ2_STAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_u32(smem + (size_t)s * OZ2_STAGE_BYTES);
+            // rows [row0, rows_blk) of the block are non-zero in this chunk
+            const int row0 = kc > 4 * rb ? 32 * (kc - 4 * rb) : 0;
+            const uint32_t idesc = oz2_idesc(rows_blk - row0);
             const uint64_t da0 = oz_desc(sa, OZ_A_BYTES / 2, 128);
-            const uint64_t db0 = oz_desc(sa + OZ_NS * OZ_A_BYTES, OZ2_B_BYTES / 2, 128);
+            const uint64_t db0 = oz_desc(sa + OZ_NS * OZ_A_BYTES + row0 * 16, OZ2_B_BYTES / 2, 128);
+            const uint32_t td = tmem + (uint32_t)row0;
             const uint32_t first = kc > 0 ? 1u : 0u;
             if (pass == 0) {
 #pragma unroll
               for (int g = 0; g < 4; g++) {
 #pragma unroll
                 for (int p = 0; p <= g; p++)
-                  oz2_mma(tmem + (uint32_t)(g * OZ2_ROWS), da0 + (uint64_t)((p * OZ_A_BYTES) >> 4),
-                          db0 + (uint64_t)(((g - p) * OZ2_B_BYTES) >> 4), p > 0 ? 1u : first);
+                  oz2_mma(td + (uint32_t)(g * OZ2_ROWS), da0 + (uint64_t)((p * OZ_A_BYTES) >> 4),
+                          db0 + (uint64_t)(((g - p) * OZ2_B_BYTES) >> 4), idesc, p > 0 ? 1u : first);
               }
             } else {
 #pragma unroll
               for (int g = 4; g < OZ_NS; g++) {
 #pragma unroll
                 for (int p = 0; p <= g; p++)
-                  oz2_mma(tmem + (uint32_t)((g - 4) * OZ2_ROWS), da0 + (uint64_t)((p * OZ_A_BYTES) >> 4),
-                          db0 + (uint64_t)(((g - p) * OZ2_B_BYTES) >> 4), p > 0 ? 1u : first);
+                  oz2_mma(td + (uint32_t)((g - 4) * OZ2_ROWS), da0 + (uint64_t)((p * OZ_A_BYTES) >> 4),
+                          db0 + (uint64_t)(((g - p) * OZ2_B_BYTES) >> 4), idesc, p > 0 ? 1u : first);
               }
             }
             oz_commit(&empty[s]);
@@ -339,12 +363,13 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
     double ssq = 0.0;
     for (int r = 0; r < n_rb; r++) {
       const int rb = my_rb[r];
+      const int ncols = min(OZ2_EPI_COLS, oz2_rows_blk(rb, n_train));   // columns the MMAs wrote
       // pass 1: hi = S0 + S1/256 + S2/256^2 + S3/256^3 (exact), parked per (column, candidate)
       oz_wait(tmem_full, t & 1);
       t++;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cc = 0; cc < OZ2_EPI_COLS; cc += 16) {
+      for (int cc = 0; cc < ncols; cc += 16) {
         uint32_t v[4][16];
 #pragma unroll
         for (int g = 0; g < 4; g++) OZ_TMEM_LD16(lane_base + (uint32_t)(g * OZ2_ROWS + cc), v[g]);
@@ -364,7 +389,7 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
       t++;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cc = 0; cc < OZ2_EPI_COLS; cc += 16) {
+      for (int cc = 0; cc < ncols; cc += 16) {
         uint32_t v[3][16];
 #pragma unroll
         for (int g = 0; g < 3; g++) OZ_TMEM_LD16(lane_base + (uint32_t)(g * OZ2_ROWS + cc), v[g]);
@@ -688,7 +713,7 @@ void ozaki_contract(gpry_state* st, const uint8_t* Ksl, int tiles, int chunk_can
   if (st->oz_rows == OZ2_ROWS)
     oz2_contract_kernel<<<std::min(st->n_sm, st->oz_splits * tiles), OZ_THREADS, OZ2_SMEM, s>>>(
         Ksl, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p, counts, st->oz_max_rb,
-        st->oz_park.p, st->ssqp.p, chunk_cands, st->oz_splits, tiles);
+        st->oz_park.p, st->ssqp.p, chunk_cands, st->oz_splits, tiles, st->N);
   else
     oz_contract_kernel<<<grid, OZ_THREADS, OZ_SMEM, s>>>(
         Ksl, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p, counts, st->oz_max_rb,

@@ -1179,7 +1179,7 @@ void predict_pipeline(gpry_state* st, const double* dX, int64_t M, bool want_mea
         finish_select_kernel<<<(n + 255) / 256, 256, 0, s>>>(fin, st->ssqp.p, row_splits, a);
         GPRY_CUDA(cudaGetLastError());
       }
-      if (++r.pending >= r.max_pending) select_compact(st, s);
+      if (++r.pending >= r.max_pending || r.first) select_compact(st, s);
     } else if (!fused) {
       TimedScope ts(st, s, T_FINISH);
       finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(fin, want_var ? st->ssqp.p : nullptr,

@@ -60,6 +60,8 @@ struct EventPair {
 struct SelectRun {
   bool on = false;
   int Kp = 0, cap = 0, cur = 0;
+  bool first = true;          // no compaction yet in this run
+  int chunk_cands = 0;        // largest chunk (upper bound of the records one chunk can append)
   int pending = 0;            // chunks appended since the last compaction
   int max_pending = 0;        // compaction period (the buffer holds K' + that many chunks)
   int64_t gbase = 0;          // global index (idx_offset included) of row 0 of the current block

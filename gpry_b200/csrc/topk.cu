@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(TK_THREADS)
 topk_rec_kernel(const double* __restrict__ keys_in, const int64_t* __restrict__ gidx_in,
                 const int* __restrict__ pos_in, const unsigned long long* __restrict__ count_ptr,
                 int64_t n, int Kp, double* __restrict__ keys_out, int64_t* __restrict__ gidx_out,
-                int* __restrict__ pos_out) {
+                int* __restrict__ pos_out, const unsigned long long* __restrict__ done_flag) {
+  if (done_flag && *done_flag != 0ull) return;
   extern __shared__ __align__(16) unsigned char tk_smem[];
   uint64_t* sk = reinterpret_cast<uint64_t*>(tk_smem);
   int64_t* si = reinterpret_cast<int64_t*>(tk_smem + TK_E * 8);
@@ -178,6 +179,78 @@ topk_rec_kernel(const double* __restrict__ keys_in, const int64_t* __restrict__ 
   }
 }
 
+// Fast path of a compaction: at most 4096 records in the buffer (the usual case once the
+// threshold is set) -> one block sorts them, writes the K' best to the other buffer and updates
+// count / threshold; ctl[3] tells the general chain behind it whether it still has to run.
+__global__ void __launch_bounds__(TK_THREADS)
+select_compact_small_kernel(const double* __restrict__ a_in, const int64_t* __restrict__ i_in,
+                            const double* __restrict__ m_in, const double* __restrict__ s_in,
+                            int Kp, double* __restrict__ a_out, int64_t* __restrict__ i_out,
+                            double* __restrict__ m_out, double* __restrict__ s_out,
+                            unsigned long long* __restrict__ ctl) {
+  extern __shared__ __align__(16) unsigned char tk_smem[];
+  uint64_t* sk = reinterpret_cast<uint64_t*>(tk_smem);
+  int64_t* si = reinterpret_cast<int64_t*>(tk_smem + TK_E * 8);
+  int* sp = reinterpret_cast<int*>(tk_smem + TK_E * 16);
+  const int tid = threadIdx.x;
+  const unsigned long long count = ctl[0];
+  if (count > (unsigned long long)TK_E) {
+    if (tid == 0) ctl[3] = 0ull;
+    return;
+  }
+  const int n = (int)count;
+  for (int e = tid; e < TK_E; e += TK_THREADS) {
+    if (e < n) {
+      sk[e] = sortable_key(a_in[e]);
+      si[e] = i_in[e];
+      sp[e] = e;
+    } else {
+      sk[e] = 0ull;
+      si[e] = INT64_MAX;
+      sp[e] = -1;
+    }
+  }
+  __syncthreads();
+  // smallest power of two >= n is enough to sort (the tail is all "empty", already last)
+  int span = 2;
+  while (span < n) span <<= 1;
+  for (int size = 2; size <= span; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int e = tid; e < span / 2; e += TK_THREADS) {
+        int lo = 2 * e - (e & (stride - 1));
+        int hi = lo + stride;
+        bool up = ((lo & size) == 0);
+        uint64_t ka = sk[lo], kb = sk[hi];
+        int64_t ia = si[lo], ib = si[hi];
+        bool swap = up ? before(kb, ib, ka, ia) : before(ka, ia, kb, ib);
+        if (swap) {
+          int pa = sp[lo], pb = sp[hi];
+          sk[lo] = kb; si[lo] = ib; sp[lo] = pb;
+          sk[hi] = ka; si[hi] = ia; sp[hi] = pa;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int e = tid; e < Kp; e += TK_THREADS) {
+    const int p = sp[e];
+    if (p >= 0) {
+      a_out[e] = a_in[p];
+      m_out[e] = m_in[p];
+      s_out[e] = s_in[p];
+      i_out[e] = si[e];
+    } else {
+      i_out[e] = INT64_MAX;
+    }
+  }
+  if (tid == 0) {
+    const unsigned long long kept = count < (unsigned long long)Kp ? count : (unsigned long long)Kp;
+    ctl[0] = kept;
+    ctl[1] = kept == (unsigned long long)Kp ? sk[Kp - 1] : 0ull;
+    ctl[3] = 1ull;
+  }
+}
+
 // the K' best (sorted) -> front of the other record buffer; count = min(count, K'); tau
 __global__ void __launch_bounds__(1024)
 select_gather_kernel(const double* __restrict__ keys, const int64_t* __restrict__ gidx,
@@ -186,6 +259,7 @@ select_gather_kernel(const double* __restrict__ keys, const int64_t* __restrict_
                      double* __restrict__ a_out, int64_t* __restrict__ i_out,
                      double* __restrict__ m_out, double* __restrict__ s_out,
                      unsigned long long* __restrict__ ctl) {
+  if (ctl[3] != 0ull) return;        // the single-block fast path has done it
   const unsigned long long count = ctl[0];
   for (int e = threadIdx.x; e < Kp; e += blockDim.x) {
     const int p = pos[e];
@@ -212,7 +286,9 @@ void select_begin(gpry_state* st, int Kp, int chunk_cands, cudaStream_t s) {
   r.Kp = Kp;
   r.cur = 0;
   r.pending = 0;
-  r.max_pending = 16;
+  r.first = true;              // compact right after the first chunk: sets the threshold early
+  r.max_pending = 64;
+  r.chunk_cands = chunk_cands;
   r.cap = Kp + r.max_pending * chunk_cands;
   for (int b = 0; b < 2; b++) {
     st->sel_acq[b].reserve(r.cap);
@@ -229,14 +305,23 @@ void select_compact(gpry_state* st, cudaStream_t s) {
   if (r.pending == 0) return;
   TimedScope ts(st, s, T_TOPK, 0);
   const int Kp = r.Kp;
-  int64_t n = r.cap;
+  const int o = r.cur ^ 1;
+  const size_t smem = (size_t)TK_E * 20;
+  GPRY_CUDA(cudaFuncSetAttribute(select_compact_small_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  select_compact_small_kernel<<<1, TK_THREADS, smem, s>>>(
+      st->sel_acq[r.cur].p, st->sel_idx[r.cur].p, st->sel_mean[r.cur].p, st->sel_std[r.cur].p, Kp,
+      st->sel_acq[o].p, st->sel_idx[o].p, st->sel_mean[o].p, st->sel_std[o].p, st->sel_ctl.p);
+  GPRY_CUDA(cudaGetLastError());
+  st->n_launches += 1;
+  // general chain (no-ops when the fast path did it): sized by what can be in the buffer
+  int64_t n = std::min<int64_t>(r.cap, (int64_t)Kp + (int64_t)r.pending * r.chunk_cands);
   int64_t nblocks = (n + TK_E - 1) / TK_E;
   for (int b = 0; b < 2; b++) {
     st->tk_keys[b].reserve((size_t)nblocks * Kp);
     st->tk_idx[b].reserve((size_t)nblocks * Kp);
     st->tk_pos[b].reserve((size_t)nblocks * Kp);
   }
-  const size_t smem = (size_t)TK_E * 20;
   GPRY_CUDA(cudaFuncSetAttribute(topk_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   const double* kin = st->sel_acq[r.cur].p;
@@ -247,7 +332,8 @@ void select_compact(gpry_state* st, cudaStream_t s) {
   while (true) {
     nblocks = (n + TK_E - 1) / TK_E;
     topk_rec_kernel<<<(unsigned)nblocks, TK_THREADS, smem, s>>>(
-        kin, iin, pin, cnt, n, Kp, st->tk_keys[lvl].p, st->tk_idx[lvl].p, st->tk_pos[lvl].p);
+        kin, iin, pin, cnt, n, Kp, st->tk_keys[lvl].p, st->tk_idx[lvl].p, st->tk_pos[lvl].p,
+        st->sel_ctl.p + 3);
     GPRY_CUDA(cudaGetLastError());
     st->n_launches += 1;
     kin = st->tk_keys[lvl].p;
@@ -258,7 +344,6 @@ void select_compact(gpry_state* st, cudaStream_t s) {
     n = nblocks * Kp;
     lvl ^= 1;
   }
-  const int o = r.cur ^ 1;
   select_gather_kernel<<<1, 1024, 0, s>>>(kin, iin, pin, Kp, st->sel_acq[r.cur].p,
                                           st->sel_mean[r.cur].p, st->sel_std[r.cur].p,
                                           st->sel_acq[o].p, st->sel_idx[o].p, st->sel_mean[o].p,
@@ -267,6 +352,7 @@ void select_compact(gpry_state* st, cudaStream_t s) {
   st->n_launches += 1;
   r.cur = o;
   r.pending = 0;
+  r.first = false;
 }
 
 // final compaction; returns the number of records (<= K'), which sit sorted at the front of
@@ -320,7 +406,8 @@ void merge_records(gpry_state* st, const double* rec, int n, int R, int Kq, doub
   while (true) {
     nblocks = (m + TK_E - 1) / TK_E;
     topk_rec_kernel<<<(unsigned)nblocks, TK_THREADS, smem, s>>>(
-        kin, iin, pin, nullptr, m, Kq, st->tk_keys[lvl].p, st->tk_idx[lvl].p, st->tk_pos[lvl].p);
+        kin, iin, pin, nullptr, m, Kq, st->tk_keys[lvl].p, st->tk_idx[lvl].p, st->tk_pos[lvl].p,
+        nullptr);
     GPRY_CUDA(cudaGetLastError());
     kin = st->tk_keys[lvl].p;
     iin = st->tk_idx[lvl].p;
