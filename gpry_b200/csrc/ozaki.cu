@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace gpry {
@@ -241,7 +242,7 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
                     const double* __restrict__ row_scale, const int* __restrict__ rb_list,
                     const int* __restrict__ rb_count, int max_rb, double* __restrict__ park,
                     double* __restrict__ ssqp, int chunk_cands, int n_splits, int n_tiles,
-                    int n_train) {
+                    int n_train, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)OZ2_STAGES * OZ2_STAGE_BYTES);
   uint64_t* empty = full + OZ2_STAGES;
@@ -290,6 +291,15 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
             const int s = it % OZ2_STAGES;
             oz_wait(&empty[s], ((it / OZ2_STAGES) & 1) ^ 1);
             uint8_t* dst = smem + (size_t)s * OZ2_STAGE_BYTES;
+            if (dbg & 1) {                 // (timing experiments: no operand traffic, wrong results)
+              oz_arrive(&full[s]);
+              continue;
+            }
+            if (dbg & 8) {                 // (timing experiments: no V traffic)
+              mbar_expect_tx(&full[s], nd * OZ_A_BYTES);
+              tma_bulk_g2s(dst, Abase + (size_t)kc * (OZ_NS * OZ_A_BYTES), nd * OZ_A_BYTES, &full[s]);
+              continue;
+            }
             mbar_expect_tx(&full[s], nd * (OZ_A_BYTES + OZ2_B_BYTES));
             tma_bulk_g2s(dst, Abase + (size_t)kc * (OZ_NS * OZ_A_BYTES), nd * OZ_A_BYTES, &full[s]);
             tma_bulk_g2s(dst + OZ_NS * OZ_A_BYTES, Bbase + (size_t)kc * (OZ_NS * OZ2_B_BYTES),
@@ -320,7 +330,7 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
             const uint32_t sa = smem_u32(smem + (size_t)s * OZ2_STAGE_BYTES);
             // rows [row0, rows_blk) of the block are non-zero in this chunk
             const int row0 = kc > 4 * rb ? 32 * (kc - 4 * rb) : 0;
-            const uint32_t idesc = oz2_idesc(rows_blk - row0);
+            const uint32_t idesc = oz2_idesc((dbg & 2) ? 64 : rows_blk - row0);
             const uint64_t da0 = oz_desc(sa, OZ_A_BYTES / 2, 128);
             const uint64_t db0 = oz_desc(sa + OZ_NS * OZ_A_BYTES + row0 * 16, OZ2_B_BYTES / 2, 128);
             const uint32_t td = tmem + (uint32_t)row0;
@@ -363,7 +373,7 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
     double ssq = 0.0;
     for (int r = 0; r < n_rb; r++) {
       const int rb = my_rb[r];
-      const int ncols = min(OZ2_EPI_COLS, oz2_rows_blk(rb, n_train));   // columns the MMAs wrote
+      const int ncols = (dbg & 4) ? 16 : min(OZ2_EPI_COLS, oz2_rows_blk(rb, n_train));   // columns the MMAs wrote
       // pass 1: hi = S0 + S1/256 + S2/256^2 + S3/256^3 (exact), parked per (column, candidate)
       oz_wait(tmem_full, t & 1);
       t++;
@@ -705,6 +715,15 @@ size_t ozaki_kslices_bytes(const gpry_state* st, int tiles) {
   return (size_t)tiles * (st->Npad / OZ_KC) * OZ_NS * OZ_A_BYTES;
 }
 
+static int oz_dbg() {      // GPRY_B200_OZ_DBG: timing experiments only (results are wrong)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GPRY_B200_OZ_DBG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 // ssqp[split][chunk_cands] for `tiles` candidate tiles whose digits are in Ksl
 void ozaki_contract(gpry_state* st, const uint8_t* Ksl, int tiles, int chunk_cands,
                     cudaStream_t s) {
@@ -713,7 +732,7 @@ void ozaki_contract(gpry_state* st, const uint8_t* Ksl, int tiles, int chunk_can
   if (st->oz_rows == OZ2_ROWS)
     oz2_contract_kernel<<<std::min(st->n_sm, st->oz_splits * tiles), OZ_THREADS, OZ2_SMEM, s>>>(
         Ksl, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p, counts, st->oz_max_rb,
-        st->oz_park.p, st->ssqp.p, chunk_cands, st->oz_splits, tiles, st->N);
+        st->oz_park.p, st->ssqp.p, chunk_cands, st->oz_splits, tiles, st->N, oz_dbg());
   else
     oz_contract_kernel<<<grid, OZ_THREADS, OZ_SMEM, s>>>(
         Ksl, st->oz_Vs.p, st->Npad / OZ_KC, st->oz_scale.p, st->oz_rb.p, counts, st->oz_max_rb,

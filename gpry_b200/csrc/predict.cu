@@ -52,19 +52,34 @@ __device__ __forceinline__ void oz_push_digits(double kv, double slice_scale /* 
                                                uint32_t (&packs)[OZ_NS][4], int q4, int jj) {
   const double xs = kv * slice_scale;
   const double m1 = xs + 6755399441055744.0;
-  int hi = __double2loint(m1);
+  const int hi = __double2loint(m1);
   const double rem = xs - (m1 - 6755399441055744.0);    // exact, |rem| <= 0.5
-  int lo = __double2loint(fma(rem, 16777216.0, 6755399441055744.0));
-  const uint32_t sel = 0x3210u ^ ((0x4u ^ (uint32_t)jj) << (4 * jj));   // byte jj <- digit
-  int dg;
-  dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[6][q4] = __byte_perm(packs[6][q4], dg, sel);
-  dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[5][q4] = __byte_perm(packs[5][q4], dg, sel);
-  dg = (int)(signed char)lo; lo = (lo - dg) >> 8; packs[4][q4] = __byte_perm(packs[4][q4], dg, sel);
-  hi += lo;                                             // carry out of the low half
-  dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[3][q4] = __byte_perm(packs[3][q4], dg, sel);
-  dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[2][q4] = __byte_perm(packs[2][q4], dg, sel);
-  dg = (int)(signed char)hi; hi = (hi - dg) >> 8; packs[1][q4] = __byte_perm(packs[1][q4], dg, sel);
-  packs[0][q4] = __byte_perm(packs[0][q4], hi, sel);
+  const int lo = __double2loint(fma(rem, 16777216.0, 6755399441055744.0));
+  // Balanced digits without a digit-by-digit carry chain: with B = 0x80 in each of the six low
+  // byte positions, the bytes of W = t + B are the digits plus 128, so (byte ^ 0x80) read as a
+  // signed byte IS the balanced digit (their weighted sum is t + B - B = t, digits in
+  // [-128, 127], and that representation is unique); bits 48.. of W are the top digit as is.
+  uint32_t wl, wh;
+  asm("{\n\t.reg .u32 t0, t1;\n\t"
+      "add.cc.u32 t0, %2, 0x80808080;\n\t"      // sign-extended lo + B
+      "addc.u32 t1, %3, 0x8080;\n\t"
+      "add.cc.u32 %0, t0, %4;\n\t"              // + hi 2^24
+      "addc.u32 %1, t1, %5;\n\t}"
+      : "=r"(wl), "=r"(wh)
+      : "r"(lo), "r"(lo >> 31), "r"((uint32_t)hi << 24), "r"(hi >> 8));
+  wl ^= 0x80808080u;
+  wh ^= 0x00008080u;
+  // byte jj of packs[p][q4] <- digit p  (digit 6 = byte 0 of wl ... digit 0 = byte 2 of wh)
+  const uint32_t keep = 0x3210u & ~(0xFu << (4 * jj));
+#define OZ_SEL(b) (keep | ((4u + (b)) << (4 * jj)))
+  packs[6][q4] = __byte_perm(packs[6][q4], wl, OZ_SEL(0u));
+  packs[5][q4] = __byte_perm(packs[5][q4], wl, OZ_SEL(1u));
+  packs[4][q4] = __byte_perm(packs[4][q4], wl, OZ_SEL(2u));
+  packs[3][q4] = __byte_perm(packs[3][q4], wl, OZ_SEL(3u));
+  packs[2][q4] = __byte_perm(packs[2][q4], wh, OZ_SEL(0u));
+  packs[1][q4] = __byte_perm(packs[1][q4], wh, OZ_SEL(1u));
+  packs[0][q4] = __byte_perm(packs[0][q4], wh, OZ_SEL(2u));
+#undef OZ_SEL
 }
 // [tile][k-chunk of 32][digit][k16 (2)][candidate (128)][16 B]: the shared-memory image of the
 // K-major operand of tcgen05.mma kind::i8

@@ -53,9 +53,9 @@ def test_selection_equals_full_sort(dev, M, Kp):
     assert np.array_equal(idx - 7, order)
     # (values: the scoring call may take the latency path (M <= 64) or the contraction's fused
     # epilogue where the selection runs the tiled kernels: same numbers to round-off)
-    assert np.allclose(a, acq[order], rtol=1e-12, atol=1e-12)
-    assert np.allclose(m, mean[order], rtol=1e-12, atol=1e-12 * st.y_std)
-    assert np.allclose(s, std[order], rtol=1e-11, atol=1e-12 * st.y_std)
+    assert np.allclose(a, acq[order], rtol=1e-10, atol=1e-10)
+    assert np.allclose(m, mean[order], rtol=1e-11, atol=1e-11 * st.y_std)
+    assert np.allclose(s, std[order], rtol=1e-10, atol=1e-11 * st.y_std)
     assert np.array_equal(Xo, Xc[order])
 
 
@@ -118,10 +118,10 @@ def test_masks_ties_and_nan(dev):
         a, idx, m, s, _ = dev.predict_logexp_topk(Xc, zeta, st.noise_level, st.y_max, Kp)
         order = reference_order(acq, Kp)
         assert np.array_equal(idx, order)
-        assert np.allclose(a, acq[order], rtol=1e-12, atol=1e-12, equal_nan=True)
+        assert np.allclose(a, acq[order], rtol=1e-10, atol=1e-10, equal_nan=True)
         assert np.array_equal(np.isfinite(a), np.isfinite(acq[order]))
-        assert np.allclose(m, mean[order], rtol=1e-12, atol=1e-12 * st.y_std, equal_nan=True)
-        assert np.allclose(s, std[order], rtol=1e-11, atol=1e-12 * st.y_std, equal_nan=True)
+        assert np.allclose(m, mean[order], rtol=1e-11, atol=1e-11 * st.y_std, equal_nan=True)
+        assert np.allclose(s, std[order], rtol=1e-10, atol=1e-11 * st.y_std, equal_nan=True)
     finally:
         dev.set_trust_region(None)
 
