@@ -472,6 +472,9 @@ def run_ours(args):
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0 = torch.cuda.current_stream()
+        dev.bcast_state(0, stream=s0)      # first use of the communicator: connection set-up
+        torch.cuda.synchronize()
+        dist.barrier()
         e0.record()
         dev.bcast_state(0, stream=s0)
         e1.record()

@@ -59,14 +59,18 @@ class LogExp:
             mask = (var > 0) & np.isfinite(mu)
             values = np.where(mask, self.f(mu, std, gp.y_max, noise_var, self.zeta), -np.inf)
             if np.array(std_grad).ndim > 1:
-                grad = np.zeros_like(std_grad)
-                if np.any(mask):
-                    # (the reference's many-point branch, :996-1001, is unreachable there
-                    # and lacks this broadcast over the dimensions)
-                    grad[mask] = np.array(std_grad)[mask] / (std[mask] - noise_var)[:, None] \
-                        + 2 * self.zeta * np.array(mu_grad)[mask]
-                if np.any(~mask):
-                    grad[~mask] = np.inf
+                # Row by row the rule of the one-point branch (:1002-1007): a finite gradient
+                # wherever std > sigma_n -- also for a row whose MEAN is masked (outside the
+                # trust region: value -inf, gradient still defined), so that a restart sees the
+                # same numbers whether it is evaluated alone or in a batch.  (The reference's
+                # own many-point branch, :996-1001, is unreachable there and lacks this
+                # broadcast over the dimensions.)
+                std_grad, mu_grad = np.array(std_grad), np.array(mu_grad)
+                fin = std > noise_var
+                grad = np.full_like(std_grad, np.inf)
+                if np.any(fin):
+                    grad[fin] = std_grad[fin] / (std[fin] - noise_var)[:, None] \
+                        + 2 * self.zeta * mu_grad[fin]
             elif std[0] > noise_var:
                 grad = std_grad / (std[0] - noise_var) + 2 * self.zeta * mu_grad
             else:

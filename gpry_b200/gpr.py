@@ -92,7 +92,7 @@ class GaussianProcessRegressor:
                  length_scale_prior=[1e-3, 1e1], noise_level=1e-2, clip_factor=1.1,
                  optimizer="fmin_l_bfgs_b", n_restarts_optimizer=0,
                  preprocessing_X=None, preprocessing_y=None,
-                 account_for_inf=None, inf_threshold="20s", keep_min_finite=None,
+                 account_for_inf="SVM", inf_threshold="20s", keep_min_finite=None,
                  trust_region_factor=None, trust_region_nstd=None,
                  bounds=None, random_state=None, verbose=1, device=None, contraction=None):
         self.n_last_appended = 0
@@ -606,7 +606,13 @@ class GaussianProcessRegressor:
                 kind, self.X_train_, noise2, self.y_train_, theta, want_L=False, want_V=False,
                 keep_on_device=True)
         if info != 0:
+            # nothing of the previous (smaller) factorisation may survive next to the new
+            # training set: a later predict must fail with "no valid factorisation"
             self._fact_sig = None
+            self._L = self._V = None
+            self.alpha_ = None
+            self._factor_resident = False
+            self._dev_dirty = True
             raise np.linalg.LinAlgError(
                 "The kernel, %s, is not returning a positive definite matrix. Try gradually "
                 "increasing the 'noise_level' parameter of your GaussianProcessRegressor "
@@ -711,6 +717,9 @@ class GaussianProcessRegressor:
             raise ValueError("Mean grad and std grad not implemented for n_samples > 1")
         X = self._as_2d(X, validate)
         impose_trust_region = self.trust_bounds is not None and not ignore_trust_region
+        if self.X_train_ is None:
+            return self._predict_from_prior(X, return_std, return_mean_grad, return_std_grad,
+                                            impose_trust_region)
         clf = self.infinities_classifier
         clf_on_device = self._classifier_on_device()
         host_clf = clf is not None and not clf_on_device
@@ -783,6 +792,25 @@ class GaussianProcessRegressor:
             return y_mean, grad_mean
         return y_mean
 
+    def _predict_from_prior(self, X, return_std, return_mean_grad, return_std_grad,
+                            impose_trust_region):
+        """Never fit to data: the GP prior, gpr.py:1111-1133 (zero mean, std = sqrt(k(x, x)),
+        zero gradients).  The reference's own guard is ``hasattr(self, "X_train_")``, which its
+        constructor makes always true (gpr.py:371), so there the branch is dead and an unfitted
+        ``predict`` fails inside the kernel call; here the documented behaviour is served."""
+        X = np.asarray(X, dtype=float)
+        y_mean = np.zeros(X.shape[0])
+        if impose_trust_region:
+            y_mean[np.logical_not(is_in_bounds(X, self.trust_bounds))] = self.minus_inf_value
+        out = [y_mean]
+        if return_std:
+            out.append(np.sqrt(self.kernel.diag(X)))
+        if return_mean_grad:
+            out.append(np.zeros_like(X))
+            if return_std and return_std_grad:
+                out.append(np.zeros_like(X))
+        return out[0] if len(out) == 1 else tuple(out)
+
     def predict_grad_batch(self, X, return_std_grad=True, validate=True,
                            ignore_trust_region=False):
         """Row-wise equivalent of ``predict(x, return_std=True, return_mean_grad=True,
@@ -822,6 +850,8 @@ class GaussianProcessRegressor:
         """gpr.py:1275-1352 (no trust region)."""
         self.n_eval += len(X)
         X = self._as_2d(X, validate)
+        if self.X_train_ is None:       # GP prior, gpr.py:1303-1305
+            return np.sqrt(self.kernel.diag(np.asarray(X, dtype=float)))
         clf = self.infinities_classifier
         finite = None
         if clf is not None and not self._classifier_on_device():

@@ -173,6 +173,34 @@ def fit_case(gpry):
           "n_eval_loglike", gpr.n_eval_loglike)
 
 
+def fit_case_d8(gpry):
+    """A second reference fit (gpr.py:883-994): d = 8, N = 300, 6 restarts (the first from the
+    kernel's initial theta is not available to an unfitted regressor: all six are prior draws)."""
+    from gpry.preprocessing import Normalize_bounds, Normalize_y
+    import warnings
+    rng = np.random.default_rng(22)
+    d, N, n_restarts = 8, 300, 6
+    bounds = np.array([[0.0, 1.0]] * d)
+    X = rng.uniform(size=(N, d))
+    y = target(X)
+    gpr = gpry.gpr.GaussianProcessRegressor(
+        kernel="RBF", bounds=bounds, noise_level=1e-2, n_restarts_optimizer=n_restarts,
+        preprocessing_X=Normalize_bounds(bounds), preprocessing_y=Normalize_y(),
+        account_for_inf=None, random_state=7, verbose=0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gpr.append_to_data(X, y, fit_gpr=True)
+    Xc = rng.uniform(size=(64, d))
+    mean, std = gpr.predict(Xc, return_std=True, validate=False)
+    np.savez_compressed(os.path.join(OUT, "fit_rbf_d8_n300.npz"), X_train=X, y_train=y,
+                        bounds=bounds, theta_opt=gpr.kernel_.theta, n_restarts=n_restarts,
+                        lml_opt=gpr.log_marginal_likelihood_value_,
+                        n_eval_loglike=gpr.n_eval_loglike, Xc=Xc, mean=mean, std=std,
+                        kernel_bounds=gpr.kernel_.bounds, theta_init=gpr.kernel.theta)
+    print("fit_rbf_d8_n300: theta_opt", gpr.kernel_.theta, "lml",
+          gpr.log_marginal_likelihood_value_, "n_eval_loglike", gpr.n_eval_loglike)
+
+
 def loop_case(gpry):
     """BASELINE config #1 in miniature (examples/readme_example.py): an active-learning loop
     on a 2-D curved log-likelihood with the reference's own pieces -- predict, LogExp.f,
@@ -297,6 +325,9 @@ def config_cases(gpry, which=("C", "D", "E")):
 def main():
     os.makedirs(OUT, exist_ok=True)
     gpry = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "fit_d8":
+        fit_case_d8(gpry)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "configs":
         config_cases(gpry, tuple(sys.argv[2:]) or ("C", "D", "E"))
         return
@@ -317,6 +348,7 @@ def main():
     extra_cases(gpry)
     nonpd_case(gpry)
     fit_case(gpry)
+    fit_case_d8(gpry)
     loop_case(gpry)
     config_cases(gpry)
 

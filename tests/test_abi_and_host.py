@@ -174,6 +174,41 @@ def test_unpickled_regressor_uses_the_local_gpu(monkeypatch):
     assert deepcopy(g2).device == 1
 
 
+def test_fit_start_points_like_reference(monkeypatch):
+    """The restart points of ``fit_gpr_hyperparameters`` (gpr.py:970-978): the first from the
+    current theta when the regressor has been fitted before, the others ``rng.uniform`` over the
+    LOG-bounds in loop order from ``check_random_state(random_state)`` -- drawn here exactly as
+    the reference (and sklearn) would, so that a fit is reproducible against it."""
+    from gpry_b200.gpr import GaussianProcessRegressor
+    bounds = np.array([[0.0, 1.0]] * 3)
+    seen = {}
+
+    def fake_lockstep(self, theta_initials, hyper_bounds):
+        seen["starts"] = [np.array(t) for t in theta_initials]
+        return [(np.array(t), float(i)) for i, t in enumerate(theta_initials)]
+
+    monkeypatch.setattr(GaussianProcessRegressor, "_lockstep_optimization", fake_lockstep)
+    monkeypatch.setattr(GaussianProcessRegressor, "_update_model", lambda self: self)
+    g = GaussianProcessRegressor(kernel="RBF", bounds=bounds, verbose=0, random_state=7,
+                                 account_for_inf=None)
+    g.fit_gpr_hyperparameters(n_restarts=5)                  # never fitted: all five are draws
+    lo, hi = g.kernel.bounds[:, 0], g.kernel.bounds[:, 1]
+    rs = np.random.RandomState(7)
+    expect = [rs.uniform(lo, hi) for _ in range(5)]
+    assert all(np.array_equal(a, b) for a, b in zip(seen["starts"], expect))
+    assert np.allclose(g.kernel_.theta, expect[0], rtol=1e-14) and g.fitted   # argmin of the fakes
+    # fitted before: restart 0 = current theta, then four draws from a FRESH generator of the seed
+    g.fit_gpr_hyperparameters(n_restarts=5)
+    rs = np.random.RandomState(7)
+    assert np.allclose(seen["starts"][0], expect[0], rtol=1e-14)
+    assert all(np.array_equal(a, rs.uniform(lo, hi)) for a in seen["starts"][1:])
+    # a Generator as random_state is used as is (what the restart-parallel fit hands each rank)
+    g.random_state = np.random.default_rng(3)
+    g.fit_gpr_hyperparameters(n_restarts=3, start_from_current=False)
+    gen = np.random.default_rng(3)
+    assert all(np.array_equal(a, gen.uniform(lo, hi)) for a in seen["starts"])
+
+
 def test_lockstep_restart_driver_without_gpu():
     """The lock-step multi-restart driver (one batched objective call per round) reaches the
     optima a serial L-BFGS-B reaches, and propagates a failing evaluation instead of hanging."""

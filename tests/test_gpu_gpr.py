@@ -203,24 +203,47 @@ def test_kernel_call(golden):
     assert scaled_err(G, Go, np.abs(Go).max()) < 1e-12
 
 
-def test_fit_like_reference():
+@pytest.mark.parametrize("name", ["fit_rbf_d2_n40", "fit_rbf_d8_n300"])
+def test_fit_like_reference(name):
+    """The hyper-parameter fit against the reference's own fit of the same data with the same
+    random state (oracle/gen_golden.py fit_case / fit_case_d8; gpr.py:883-994): same restart
+    points (pinned in test_abi_and_host.py::test_fit_start_points_like_reference), same scipy
+    L-BFGS-B.  The LML is flat along log c near these optima (length scales at their upper
+    bound, c ~ 1e4..1e5), so two evaluators that agree to 1e-12 leave the optimiser at points
+    that differ at its own stopping tolerance: theta to a few 1e-4 in log units, LML to 1e-6
+    relative, evaluation count to ~25 % (measured: 5e-5 / 2e-7 / 181 vs 199 and 1.4e-4 / 2e-8 /
+    125 vs 159).  The lock-step driver and the one-by-one driver must agree with each other
+    exactly (same evaluator, same iterates)."""
     from gpry_b200.gpr import GaussianProcessRegressor
     from gpry_b200.preprocessing import Normalize_bounds, Normalize_y
-    z = np.load(os.path.join(GOLDEN_DIR, "fit_rbf_d2_n40.npz"))
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    n_restarts = int(z["n_restarts"]) if "n_restarts" in z.files else 4
+    out = {}
     for lockstep in (True, False):
         gpr = GaussianProcessRegressor(
-            kernel="RBF", bounds=z["bounds"], noise_level=1e-2, n_restarts_optimizer=4,
+            kernel="RBF", bounds=z["bounds"], noise_level=1e-2, n_restarts_optimizer=n_restarts,
             preprocessing_X=Normalize_bounds(z["bounds"]), preprocessing_y=Normalize_y(),
             account_for_inf=None, random_state=7, verbose=0)
         assert np.allclose(gpr.kernel.theta, z["theta_init"], rtol=1e-15)
         assert np.allclose(gpr.kernel.bounds, z["kernel_bounds"], rtol=1e-15)
         gpr.append_to_data(z["X_train"], z["y_train"],
-                           fit_gpr={"n_restarts": 4, "lockstep": lockstep})
+                           fit_gpr={"n_restarts": n_restarts, "lockstep": lockstep})
         assert gpr.fitted
         ref = float(z["lml_opt"])
-        assert gpr.log_marginal_likelihood_value_ >= ref - 1e-3 * abs(ref)
-        mean = gpr.predict(z["X_train"][:5])
-        assert np.allclose(mean, z["y_train"][:5], atol=1e-2 * np.std(z["y_train"]))
+        assert abs(gpr.log_marginal_likelihood_value_ - ref) <= 1e-6 * abs(ref)
+        assert np.max(np.abs(gpr.kernel_.theta - z["theta_opt"])) < 5e-4
+        # the length scales end ON the upper bound, like the reference's
+        at_bound = z["theta_opt"][1:] == z["kernel_bounds"][1:, 1]
+        assert np.array_equal(gpr.kernel_.theta[1:][at_bound], z["theta_opt"][1:][at_bound])
+        assert abs(gpr.n_eval_loglike - int(z["n_eval_loglike"])) <= 0.3 * int(z["n_eval_loglike"])
+        sy = float(np.std(z["y_train"]))
+        mean, std = gpr.predict(z["Xc"], return_std=True)
+        assert np.max(np.abs(mean - z["mean"])) < 1e-6 * sy       # same model to optimiser accuracy
+        assert np.max(np.abs(std - z["std"])) < 1e-6 * sy
+        out[lockstep] = (np.array(gpr.kernel_.theta), gpr.log_marginal_likelihood_value_,
+                         gpr.n_eval_loglike)
+    assert np.array_equal(out[True][0], out[False][0]) and out[True][1] == out[False][1]
+    assert out[True][2] == out[False][2]
 
 
 def test_active_learning_loop_like_reference():
