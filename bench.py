@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 METRIC = "gp_predict_logexp_candidates_per_sec"
 UNIT = "candidates/s"
 FP64_DGEMM_FALLBACK_TFLOPS = 35.4   # cublasDgemm 8192^3 on this pool (profiles/r01_fp64_peaks.txt)
-PROFILE_INT8 = "r01_oz_contract_ncu.json"      # ncu --set full capture of the INT8 contraction
+PROFILE_INT8 = "r02_oz_contract_ncu.json"      # ncu --set full capture of the INT8 contraction
 PROFILE_FP64 = "r01_contract_ncu.json"         # ... and of the FP64 (DMMA) contraction
 KERNEL_INT8 = ("oz2_contract_kernel (INT8 Ozaki split, two passes of 128x128x32 tcgen05.mma "
                "kind::i8, TMEM)")

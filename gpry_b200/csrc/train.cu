@@ -32,6 +32,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cstdlib>
+
 #include "state.cuh"
 
 namespace gpry {
@@ -339,6 +341,15 @@ struct GemmArgs {
   size_t sW, sVT;
   int row_offset;
   int* info;
+  // split-K: the k range of every tile is cut into `splits` contiguous parts computed by
+  // different CTAs (gridDim.x = batch * splits); each writes its partial accumulators to
+  // `scratch`, the LAST one to arrive at the tile's counter adds all parts in part order (so
+  // the sum does not depend on the arrival order) and runs the epilogue.  Fills the GPU when a
+  // launch has fewer tiles than SMs (single factorisations) or leaves a ragged last wave.
+  int splits;
+  int batch;
+  double* scratch;      // [tile slot][split][128 x 128]
+  int* counters;        // [tile slot], zero before the launch, reset by the last arriver
 };
 
 struct GemmSmem {
@@ -371,9 +382,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
   GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = mt * TILE_ROWS, n0 = nt * TILE_ROWS;
-  const int k_lo = sg.klo_row ? m0 : 0;
-  const int nk = (g.K - k_lo) / TILE_K;
-  const size_t bz = blockIdx.x;
+  int k_lo = sg.klo_row ? m0 : 0;
+  int nk = (g.K - k_lo) / TILE_K;
+  const size_t bz = blockIdx.x % g.batch;
+  const int split = blockIdx.x / g.batch;
+  if (g.splits > 1) {       // this CTA's part of the k range
+    const int k_a = (int)((long long)nk * split / g.splits);
+    const int k_b = (int)((long long)nk * (split + 1) / g.splits);
+    k_lo += k_a * TILE_K;
+    nk = k_b - k_a;
+  }
 
   const double* Ag = sg.A + bz * sg.sA + (size_t)m0 * sg.lda + k_lo;
   const double* Bg = g.B + bz * g.sB + (size_t)n0 * g.ldb + k_lo;
@@ -425,6 +443,44 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
   }
   cp_async_wait<0>();
   __syncthreads();   // in-place segments: every warp's operand reads are done before C is written
+  if (g.splits > 1) {
+    // slot of this tile; partial accumulators as [split][register][thread] (coalesced)
+    const size_t slot = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * g.batch + bz;
+    double* part = g.scratch + (slot * g.splits + split) * (size_t)(TILE_ROWS * TILE_ROWS);
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+        __stcg(part + (size_t)((mi * 4 + ni) * 2 + 0) * G_THREADS + tid, acc[mi][ni][0]);
+        __stcg(part + (size_t)((mi * 4 + ni) * 2 + 1) * G_THREADS + tid, acc[mi][ni][1]);
+      }
+    __threadfence();
+    __syncthreads();
+    __shared__ int s_last;
+    if (tid == 0) {
+      const int old = atomicAdd(g.counters + slot, 1);
+      s_last = old == g.splits - 1;
+      if (s_last) g.counters[slot] = 0;       // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const double* all = g.scratch + slot * g.splits * (size_t)(TILE_ROWS * TILE_ROWS);
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    for (int sp = 0; sp < g.splits; sp++) {      // fixed order: parts 0, 1, ...
+      const double* q = all + (size_t)sp * (TILE_ROWS * TILE_ROWS);
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+          acc[mi][ni][0] += __ldcg(q + (size_t)((mi * 4 + ni) * 2 + 0) * G_THREADS + tid);
+          acc[mi][ni][1] += __ldcg(q + (size_t)((mi * 4 + ni) * 2 + 1) * G_THREADS + tid);
+        }
+    }
+  }
   // epilogue
   const int g8 = lane >> 2, t4 = lane & 3;
   double* Cg = sg.C + bz * sg.sC;
@@ -453,10 +509,82 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
   }
 }
 
-static void launch_gemm(const GemmArgs& g, int batch, cudaStream_t s) {
+// scratch / counters of the split-K path and the number of SMs (set by gemm_prepare)
+static double* g_split_scratch = nullptr;
+static size_t g_split_scratch_doubles = 0;
+static int* g_split_counters = nullptr;
+static size_t g_split_counters_n = 0;
+static int g_n_sm = 148;
+static int g_splitk_enabled = -1;
+
+// Parts per tile.  Measured (profiles/r02_train_ab.txt): splitting pays when a launch leaves SMs
+// idle -- fewer tiles than SMs (single factorisations: 32 tiles at N = 4000) or a ragged second
+// wave -- and costs ~3 % per part (partial accumulators written and re-read through L2), so a
+// split must win 6 % below one wave of tiles and 15 % above.  1 = whole tiles.
+static int choose_splits(int tiles, int max_nk) {
+  if (g_splitk_enabled < 0) {
+    const char* e = getenv("GPRY_B200_SPLITK");
+    g_splitk_enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!g_splitk_enabled || tiles <= 0) return 1;
+  const double need = tiles < g_n_sm ? 0.94 : 0.85;
+  double best_cost = 1e30;
+  int best = 1;
+  for (int sp = 1; sp <= 8; sp++) {
+    if (sp > 1 && max_nk / sp < 4) break;   // (a short tile may end up with empty parts: fine)
+    const int ctas = tiles * sp;
+    const double rounds = (double)((ctas + g_n_sm - 1) / g_n_sm) / sp;   // in whole-tile times
+    const double cost = rounds * (sp > 1 ? 1.0 + 0.03 * sp : 1.0);
+    if (cost < best_cost * need) {
+      best_cost = cost;
+      best = sp;
+    }
+  }
+  return best;
+}
+
+static void launch_gemm(const GemmArgs& g_in, int batch, cudaStream_t s) {
+  GemmArgs g = g_in;
   const int mt = g.seg[0].m_tiles + g.seg[1].m_tiles;
   if (mt <= 0 || g.n_tiles <= 0 || g.K <= 0 || batch <= 0) return;
-  dim3 grid(batch, mt, g.n_tiles);
+  // active tiles and the shortest k range among them
+  int tiles = 0, max_nk = 0;
+  for (int nt = 0; nt < g.n_tiles; nt++)
+    for (int m = 0; m < mt; m++) {
+      const int si = m >= g.seg[0].m_tiles ? 1 : 0;
+      const int mm = si ? m - g.seg[0].m_tiles : m;
+      if (g.lower_only && mm < nt) continue;
+      const int k_lo = g.seg[si].klo_row ? mm * TILE_ROWS : 0;
+      tiles++;
+      max_nk = std::max(max_nk, (g.K - k_lo) / TILE_K);
+    }
+  g.batch = batch;
+  g.splits = choose_splits(tiles * batch, max_nk);
+  if (g.splits > 1) {
+    const size_t slots = (size_t)g.n_tiles * mt * batch;
+    size_t need = slots * g.splits * (size_t)(TILE_ROWS * TILE_ROWS);
+    if (need > g_split_scratch_doubles) {
+      need = std::max(need + need / 2, (size_t)32 << 20);     // grow rarely (256 MB at least)
+      if (g_split_scratch) cudaFree(g_split_scratch);
+      g_split_scratch = nullptr;
+      g_split_scratch_doubles = 0;
+      if (cudaMalloc((void**)&g_split_scratch, need * 8) != cudaSuccess) {
+        cudaGetLastError();
+        g.splits = 1;                    // no room: whole tiles
+      } else {
+        g_split_scratch_doubles = need;
+      }
+    }
+    if (g.splits > 1 && slots > g_split_counters_n) {
+      if (g_split_counters) cudaFree(g_split_counters);
+      GPRY_CUDA(cudaMalloc((void**)&g_split_counters, slots * sizeof(int)));
+      GPRY_CUDA(cudaMemsetAsync(g_split_counters, 0, slots * sizeof(int), s));
+      g_split_counters_n = slots;
+    }
+    g.scratch = g_split_scratch;
+    g.counters = g_split_counters;
+  }
+  dim3 grid(batch * g.splits, mt, g.n_tiles);
   const size_t smem = g.fuse_potf2 ? std::max(sizeof(GemmSmem), POTF2_SMEM_DOUBLES * 8)
                                    : sizeof(GemmSmem);
   gemm_nt_kernel<<<grid, G_THREADS, smem, s>>>(g);
@@ -465,6 +593,10 @@ static void launch_gemm(const GemmArgs& g, int batch, cudaStream_t s) {
 static void gemm_prepare() {
   GPRY_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)std::max(sizeof(GemmSmem), POTF2_SMEM_DOUBLES * 8)));
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+    g_n_sm = n;
 }
 
 void gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N,
@@ -870,8 +1002,25 @@ static void factorize_batch(gpry_state* st, TrainBuffers& b, int kind, const dou
 // thetas per sub-batch: bounded by memory (3 Np^2 doubles each) and by what fills the GPU
 static int sub_batch(int B, int Np, bool need_grad) {
   const double per_theta = (need_grad ? 3.0 : 2.0) * Np * (double)Np * 8.0;
-  int cap = (int)std::max(1.0, std::floor(16e9 / per_theta));
-  return std::max(1, std::min(std::min(B, 16), cap));
+  const int cap = (int)std::max(1.0, std::min(48.0, std::floor(20e9 / per_theta)));
+  if (B <= cap) return B;
+  // several sub-batches: the size whose panel launches (Np / 128 tiles per theta) waste the
+  // least of their last wave on this GPU, counted over all sub-batches
+  const int tiles_per_theta = Np / NB;
+  int best = std::min(B, cap);
+  double best_cost = 1e30;
+  for (int bs = cap; bs >= std::max(1, cap / 2); bs--) {
+    double rounds = 0;
+    for (int done = 0; done < B; done += bs) {
+      const int n = std::min(bs, B - done);
+      rounds += (double)((n * tiles_per_theta + g_n_sm - 1) / g_n_sm);
+    }
+    if (rounds < best_cost) {
+      best_cost = rounds;
+      best = bs;
+    }
+  }
+  return best;
 }
 
 void factorize_device(gpry_state* st, int kind, int N, int d, const double* X_train_t,

@@ -328,6 +328,32 @@ class NORA:
                                       "sampler) and 'ensemble'; or pass X_mc from your own")
         return rng.uniform(b[:, 0], b[:, 1], size=(self.nsamples, b.shape[0]))
 
+    # ------------------------------------------------------------------ NS front-ends
+    @staticmethod
+    def logp_function(gpr, flavour="ultranest"):
+        """The surrogate log-posterior closure the reference hands to its nested samplers
+        (gp_acquisition.py:770, 784-793): ``logp(X)`` for ``X`` of shape (d,) or (M, d).
+        UltraNest calls it VECTORISED (ns_interfaces.py:448 ``"vectorized": True``), i.e. with
+        whole batches of live-point proposals: each call is one mean-only device pass
+        (``gpry_predict(what=MEAN)``, masks applied on the GPU).
+
+        ``"ultranest"``: masked rows (classifier / trust region) come back as ``-1e-300``
+        instead of ``-inf`` -- the reference swaps ``gpr.minus_inf_value`` around the call
+        (:788-792) because UltraNest cannot digest infinities; ``"polychord"`` / ``"nessai"``:
+        one point per call, returns a float (:770)."""
+        if flavour == "ultranest":
+            def logp(X):
+                prev = gpr.minus_inf_value
+                gpr.minus_inf_value = -1e-300
+                try:
+                    return gpr.predict(np.atleast_2d(X), return_std=False, validate=False)
+                finally:
+                    gpr.minus_inf_value = prev
+            return logp
+        if flavour in ("polychord", "nessai"):
+            return lambda X: gpr.predict(np.atleast_2d(X), return_std=False, validate=False)[0]
+        raise ValueError(f"unknown nested-sampler flavour {flavour!r}")
+
     # ------------------------------------------------------------------ the MC pool
     def _set_pool(self, gpr, bounds, rng, force_resample, X_mc, X_shard):
         """Decides whether this call works on a new MC sample (gp_acquisition.py:1016-1027) and

@@ -486,8 +486,9 @@ class GaussianProcessRegressor:
         """gpr.py:883-994.  Same restarts, same starting points (``rng.uniform`` over the
         log-bounds in loop order), same scipy L-BFGS-B driver per restart.  With
         ``lockstep=True`` (default) the restarts advance together and every round of
-        objective evaluations is ONE batched device call; each restart still sees exactly
-        the function values it would see alone, so the optimum is the same."""
+        objective evaluations is ONE batched device call; each restart sees the function
+        values it would see alone up to round-off (see ``gpry_b200.lockstep``), so it ends at
+        the same optimum to the optimiser's tolerance."""
         if simple:
             start_from_current = True
             n_restarts = 1

@@ -6,8 +6,11 @@ evaluates ONE point (hyper-parameters: gpr.py:944-989; acquisition: gp_acquisiti
 280-390, 503-511).  On a GPU one evaluation costs about as much as a few hundred, so here every
 restart runs the same scipy optimiser in its own thread and the objective calls of all
 still-active restarts meet at a barrier: one batched device call evaluates them together.
-The per-restart iterates are those scipy would produce on its own (same line search, same
-stopping rules): only the evaluation is shared.
+The per-restart iterates are those scipy would produce on its own from the same function
+values (same line search, same stopping rules): only the evaluation is shared.  (The values
+themselves can differ in the last bits between a batched and a one-at-a-time evaluation, e.g.
+where the training-side GEMMs split their k range for small batches; the optimiser then stops
+at points that agree to its own tolerance.)
 """
 import threading
 import warnings

@@ -76,3 +76,30 @@ def test_nora_with_ensemble_sampler():
     assert np.all(np.abs(nora._X_shard.mean(axis=0) - 0.5) < 0.05)
     assert np.all(nora._X_shard.std(axis=0) < 0.2)
     assert np.all(np.linalg.norm(X - 0.5, axis=1) < 0.6)
+
+
+def test_nested_sampler_logp_closures():
+    """The closures the reference gives its nested samplers (gp_acquisition.py:770, 784-793):
+    UltraNest's is called with batches (ns_interfaces.py:448) and must not return -inf."""
+    from conftest import load_golden
+    from gpry_b200.gp_acquisition import NORA
+    from test_gpu_gpr import make_gpr
+    g = load_golden("rbf_d8_n300")
+    gpr = make_gpr(g)
+    lo, hi = g["bounds"][:, 0], g["bounds"][:, 1]
+    gpr.trust_bounds = np.stack([lo + 0.2 * (hi - lo), hi - 0.2 * (hi - lo)], axis=1)
+    X = g["Xc"]
+    inside = np.all((X >= gpr.trust_bounds[:, 0]) & (X <= gpr.trust_bounds[:, 1]), axis=1)
+    assert 0 < inside.sum() < len(X)
+    logp = NORA.logp_function(gpr, "ultranest")
+    n0 = gpr.n_eval
+    batch = logp(X)
+    assert gpr.n_eval == n0 + len(X) and gpr.minus_inf_value == -np.inf      # restored
+    assert np.all(batch[~inside] == -1e-300) and np.all(np.isfinite(batch))
+    ref = gpr.predict(X, ignore_trust_region=True)
+    assert np.array_equal(batch[inside], ref[inside])
+    one = NORA.logp_function(gpr, "polychord")
+    i_in, i_out = np.flatnonzero(inside)[0], np.flatnonzero(~inside)[0]
+    assert isinstance(one(X[i_in]), float) and abs(one(X[i_in]) - ref[i_in]) <= 1e-12 * abs(ref[i_in])
+    assert one(X[i_out]) == -np.inf
+    assert logp(X[i_in]).shape == (1,)
