@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpry_b200.so")
+# (GPRY_B200_LIB: another build of the same library, for A/B measurements)
+LIB_PATH = os.environ.get("GPRY_B200_LIB") or os.path.join(_HERE, "libgpry_b200.so")
 
 KERNEL_KINDS = {"rbf": 0, "matern15": 1, "matern25": 2}
 X_ON_DEVICE, OUT_ON_DEVICE = 1, 2

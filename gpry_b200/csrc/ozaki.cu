@@ -237,6 +237,35 @@ __device__ __forceinline__ int oz2_nch(int rb, int rows_blk) {
   return 4 * rb + ((rows_blk + 31) >> 5);
 }
 
+// The MMAs of one k chunk of pass PASS (0: digit groups 0..3, 1: groups 4..6).  db0 describes V
+// digit 0 at the chunk's first row (k halves nd * 2048 bytes apart); digit q is 2048 bytes on.
+// PAIR: one N = 256 MMA per two consecutive V digits (idesc = the 256-column one), with the
+// accumulator-enable of the pair taken from its first group (both groups are in the same state:
+// the first product into every accumulator is the p = 0 one).
+template <int PASS, bool PAIR>
+__device__ __forceinline__ void oz2_issue_chunk(uint32_t td, uint64_t da0, uint64_t db0,
+                                                uint32_t idesc, uint32_t first) {
+  constexpr int G0 = PASS == 0 ? 0 : 4, G1 = PASS == 0 ? 3 : 6;
+  constexpr uint32_t HALF = OZ2_B_BYTES / 2;
+  const uint32_t idesc1 = oz2_idesc(OZ2_ROWS);       // (PAIR only: the odd digit left over)
+#pragma unroll
+  for (int p = 0; p <= G1; p++) {
+    const int qlo = G0 - p > 0 ? G0 - p : 0, qhi = G1 - p;
+    const uint64_t da = da0 + (uint64_t)((p * OZ_A_BYTES) >> 4);
+    const uint32_t en = p == 0 ? first : 1u;
+#pragma unroll
+    for (int q = qlo; q <= qhi; q++) {
+      const uint32_t tcol = td + (uint32_t)((p + q - G0) * OZ2_ROWS);
+      const uint64_t db = db0 + (uint64_t)((q * HALF) >> 4);
+      if (PAIR) {
+        if (((q - qlo) & 1) == 0) oz2_mma(tcol, da, db, q + 1 <= qhi ? idesc : idesc1, en);
+      } else {
+        oz2_mma(tcol, da, db, idesc, en);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__ Vs, int nKC,
                     const double* __restrict__ row_scale, const int* __restrict__ rb_list,
@@ -302,8 +331,17 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
             }
             mbar_expect_tx(&full[s], nd * (OZ_A_BYTES + OZ2_B_BYTES));
             tma_bulk_g2s(dst, Abase + (size_t)kc * (OZ_NS * OZ_A_BYTES), nd * OZ_A_BYTES, &full[s]);
-            tma_bulk_g2s(dst + OZ_NS * OZ_A_BYTES, Bbase + (size_t)kc * (OZ_NS * OZ2_B_BYTES),
-                         nd * OZ2_B_BYTES, &full[s]);
+            // V digits: global [k16][digit][row][16 B]; the stage keeps the nd digits of each k
+            // half together (pass 1: two pieces, pass 2: the whole chunk in one)
+            const uint8_t* Bsrc = Bbase + (size_t)kc * (OZ_NS * OZ2_B_BYTES);
+            uint8_t* Bdst = dst + OZ_NS * OZ_A_BYTES;
+            if (pass == 0) {
+              tma_bulk_g2s(Bdst, Bsrc, nd * (OZ2_B_BYTES / 2), &full[s]);
+              tma_bulk_g2s(Bdst + nd * (OZ2_B_BYTES / 2), Bsrc + OZ_NS * (OZ2_B_BYTES / 2),
+                           nd * (OZ2_B_BYTES / 2), &full[s]);
+            } else {
+              tma_bulk_g2s(Bdst, Bsrc, OZ_NS * OZ2_B_BYTES, &full[s]);
+            }
           }
         }
       }
@@ -330,27 +368,26 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
             const uint32_t sa = smem_u32(smem + (size_t)s * OZ2_STAGE_BYTES);
             // rows [row0, rows_blk) of the block are non-zero in this chunk
             const int row0 = kc > 4 * rb ? 32 * (kc - 4 * rb) : 0;
-            const uint32_t idesc = oz2_idesc((dbg & 2) ? 64 : rows_blk - row0);
+            const int nrows = (dbg & 2) ? 64 : rows_blk - row0;
+            const uint32_t nd = pass == 0 ? 4u : (uint32_t)OZ_NS;
+            const uint32_t half = OZ2_B_BYTES / 2;                  // one digit, one k half
             const uint64_t da0 = oz_desc(sa, OZ_A_BYTES / 2, 128);
-            const uint64_t db0 = oz_desc(sa + OZ_NS * OZ_A_BYTES + row0 * 16, OZ2_B_BYTES / 2, 128);
+            const uint64_t db0 = oz_desc(sa + OZ_NS * OZ_A_BYTES + row0 * 16, nd * half, 128);
             const uint32_t td = tmem + (uint32_t)row0;
             const uint32_t first = kc > 0 ? 1u : 0u;
+            // Full 128-row chunks: ONE MMA of N = 256 covers two consecutive V digits q, q + 1
+            // (adjacent in shared memory) against the same K* digit p, i.e. the adjacent
+            // accumulators of groups p + q and p + q + 1: 6 + 12 instructions per chunk instead of
+            // 10 + 18, and the 4 KB K* operand is read once per pair.  Narrow chunks (diagonal,
+            // ragged last block): one digit at a time, N = nrows.  (Four fully unrolled variants:
+            // every descriptor is a base plus an immediate, see DESIGN.md "MMA issue loop".)
+            const bool pair = (nrows == OZ2_ROWS) && !(dbg & 32);
             if (pass == 0) {
-#pragma unroll
-              for (int g = 0; g < 4; g++) {
-#pragma unroll
-                for (int p = 0; p <= g; p++)
-                  oz2_mma(td + (uint32_t)(g * OZ2_ROWS), da0 + (uint64_t)((p * OZ_A_BYTES) >> 4),
-                          db0 + (uint64_t)(((g - p) * OZ2_B_BYTES) >> 4), idesc, p > 0 ? 1u : first);
-              }
+              if (pair) oz2_issue_chunk<0, true>(td, da0, db0, oz2_idesc(2 * OZ2_ROWS), first);
+              else oz2_issue_chunk<0, false>(td, da0, db0, oz2_idesc(nrows), first);
             } else {
-#pragma unroll
-              for (int g = 4; g < OZ_NS; g++) {
-#pragma unroll
-                for (int p = 0; p <= g; p++)
-                  oz2_mma(td + (uint32_t)((g - 4) * OZ2_ROWS), da0 + (uint64_t)((p * OZ_A_BYTES) >> 4),
-                          db0 + (uint64_t)(((g - p) * OZ2_B_BYTES) >> 4), idesc, p > 0 ? 1u : first);
-              }
+              if (pair) oz2_issue_chunk<1, true>(td, da0, db0, oz2_idesc(2 * OZ2_ROWS), first);
+              else oz2_issue_chunk<1, false>(td, da0, db0, oz2_idesc(nrows), first);
             }
             oz_commit(&empty[s]);
           }
@@ -482,8 +519,18 @@ oz_slice_v_kernel(const double* __restrict__ Vrm, int Np, const double* __restri
   }
   const int nKC = Np / OZ_KC;
   const int b_bytes = rows_per_block * OZ_KC;      // one digit of one chunk
-  uint8_t* base = Vs + ((size_t)(j / rows_per_block) * nKC + (k0 >> 5)) * (size_t)(OZ_NS * b_bytes) +
-                  ((k0 >> 4) & 1) * (b_bytes / 2) + (j % rows_per_block) * 16;
+  uint8_t* chunk = Vs + ((size_t)(j / rows_per_block) * nKC + (k0 >> 5)) * (size_t)(OZ_NS * b_bytes);
+  if (rows_per_block == 128) {
+    // two-pass kernel: [k16 (2)][digit][row (128)][16 B] -- the rows of consecutive digits are
+    // contiguous, so ONE MMA of N = 256 can take two digits (two digit groups) at a time
+    uint8_t* base = chunk + ((k0 >> 4) & 1) * (OZ_NS * (b_bytes / 2)) + (j % rows_per_block) * 16;
+#pragma unroll
+    for (int p = 0; p < OZ_NS; p++)
+      *reinterpret_cast<uint4*>(base + (size_t)p * (b_bytes / 2)) =
+          make_uint4(packs[p][0], packs[p][1], packs[p][2], packs[p][3]);
+    return;
+  }
+  uint8_t* base = chunk + ((k0 >> 4) & 1) * (b_bytes / 2) + (j % rows_per_block) * 16;
 #pragma unroll
   for (int p = 0; p < OZ_NS; p++)
     *reinterpret_cast<uint4*>(base + (size_t)p * b_bytes) =

@@ -22,6 +22,9 @@
 //                 blocks of V are split over several CTAs for small pools, or mean only).
 #include <math.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "state.cuh"
 
 namespace gpry {
@@ -828,6 +831,18 @@ void upload_model(gpry_state* st, int kind, int N, int d, const double* X_train_
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
+// Shared-memory floor of kstar_build blocks (bytes): pads the request so that FEWER blocks fit on
+// an SM.  A chunk is 2 n_sm tiles x JS slices = 16 n_sm blocks at JS = 8: with 4 resident blocks
+// per SM that is exactly 4 waves, with the 5 the kernel's own footprint allows it is 3.2.
+// GPRY_B200_BUILD_SMEM_KB overrides (experiments).
+static size_t build_smem_floor() {
+  static long v = -1;
+  if (v < 0) {
+    const char* e = getenv("GPRY_B200_BUILD_SMEM_KB");
+    v = e ? atol(e) * 1024 : 0;
+  }
+  return (size_t)v;
+}
 template <int KIND, int WMODE>
 static void launch_build(gpry_state* st, const double* dX, int64_t M, int64_t cand0, int tiles,
                          int JS, int chunk_cands, cudaStream_t s) {
@@ -838,6 +853,7 @@ static void launch_build(gpry_state* st, const double* dX, int64_t M, int64_t ca
   const double slice_scale = 1073741824.0 / st->c;           // 2^30 / c (see kstar_build, WMODE 2)
   if (d <= MAX_DIM_REG) {
     size_t smem = ((size_t)NJ * DP + NJ + 128 * d + (d & 1)) * 8 + 16;
+    smem = std::max(smem, build_smem_floor());
 #define GPRY_LAUNCH_BUILD(DPV)                                                                \
   case DPV: {                                                                                 \
     auto kern = kstar_build_kernel<DPV, KIND, WMODE>;                                         \
@@ -888,6 +904,10 @@ static void launch_build_kind(gpry_state* st, const double* dX, int64_t M, int64
 // Largest j-split count JS (power of two) such that the per-block training slice
 // NJ = Npad / JS stays a multiple of 16, fits in shared memory and gives >= ~2 blocks/SM.
 static int choose_jsplit(const gpry_state* st, int tiles) {
+  if (const char* e = getenv("GPRY_B200_BUILD_JS")) {      // experiments
+    const int js = atoi(e);
+    if (js >= 1 && st->Npad % (js * 16) == 0) return js;
+  }
   int JS = 1;
   if (st->d > MAX_DIM_REG) {   // generic path: [NJ][DP] slice + [DP][129] candidates in smem
     int maxJSg = st->Npad / 16;
