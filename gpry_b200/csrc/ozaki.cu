@@ -52,6 +52,18 @@ __device__ __forceinline__ void oz_commit(uint64_t* bar) {
 __device__ __forceinline__ void oz_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one lane of a converged warp (elect.sync): the compiler then treats the region as run by a
+// single, known thread and issues the uniform-datapath tcgen05 instructions straight-line,
+// without an ELECT + branch loop around each of them
+__device__ __forceinline__ bool oz_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // a wait that cannot hang the GPU: traps after ~seconds
 __device__ __forceinline__ void oz_wait(uint64_t* bar, uint32_t parity) {
   for (long long it = 0; it < 400000000LL; it++)
@@ -303,7 +315,7 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {   // ---- producer
+    if (oz_elect_one()) {   // ---- producer
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int split = w % n_splits, tile = w / n_splits;
@@ -348,7 +360,7 @@ oz2_contract_kernel(const uint8_t* __restrict__ Ksl, const uint8_t* __restrict__
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {   // ---- MMA issuer
+    if (oz_elect_one()) {   // ---- MMA issuer
       int it = 0, t = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int split = w % n_splits;
@@ -572,7 +584,7 @@ __global__ void __launch_bounds__(128, 1) oz_peak_kernel(int reps) {
   const uint32_t tmem = tmem_slot;
   uint32_t phase = 0;
   for (int r = 0; r < reps; r++) {
-    if (tid == 0) {
+    if (warp == 0 && oz_elect_one()) {
       const uint64_t da0 = oz_desc(smem_u32(smem), 2048, 128);
       const uint64_t db0 = oz_desc(smem_u32(smem) + 4 * 4096, 4096, 128);
 #pragma unroll
