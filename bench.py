@@ -43,6 +43,39 @@ KERNEL_INT8 = ("oz2_contract_kernel (INT8 Ozaki split, two passes of 128x128x32 
                "kind::i8, TMEM)")
 
 
+# ------------------------------------------------------------------------------------------
+# watchdog: a multi-GPU run that stops making progress (a stuck collective on some fabric) must
+# not hang the caller: after WATCHDOG_S seconds every rank dumps its stacks to stderr, rank 0
+# prints the line with what has been measured so far ("incomplete": the section it was in), and
+# the process exits.
+# ------------------------------------------------------------------------------------------
+WATCHDOG_S = float(os.environ.get("GPRY_B200_BENCH_WATCHDOG_S", "900"))
+PARTIAL = {"section": "start"}
+_REAL_STDOUT_FD = None
+
+
+def _watchdog_fire():
+    import faulthandler
+    try:
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+    except Exception:
+        pass
+    if int(os.environ.get("RANK", "0")) == 0 and "line" in PARTIAL:
+        line = dict(PARTIAL["line"])
+        line["incomplete"] = f"watchdog after {WATCHDOG_S:.0f} s in section '{PARTIAL['section']}'"
+        fd = _REAL_STDOUT_FD if _REAL_STDOUT_FD is not None else 1
+        os.write(fd, (json.dumps(line) + "\n").encode())
+    os._exit(0 if "line" in PARTIAL else 3)
+
+
+def start_watchdog():
+    import threading
+    t = threading.Timer(WATCHDOG_S, _watchdog_fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -178,7 +211,7 @@ def run_reference(args):
                                 f"{len(top)} of one chunk (refits at N_train={N}), timed once"},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -463,18 +496,18 @@ def run_ours(args):
     gpr = bench_gpr(N, d, local)
     gpr.contraction = args.contract
     zeta, sig, ymax = float(d) ** -0.85, float(gpr.noise_level), float(gpr.y_max)
-    t_bcast_ms, bcast_diff = 0.0, None
+    t_bcast_ms, bcast_diff, comm = 0.0, None, None
     if world > 1:
-        comm = parallel.device_comm(local)
+        comm = parallel.device_comm(local)      # None: exchange through torch.distributed
+    if comm is not None:
         dev = gpr._device_state() if rank == 0 else DeviceGP(local)
         dev.comm_share(comm)
-        torch.cuda.synchronize()
-        dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0 = torch.cuda.current_stream()
         dev.bcast_state(0, stream=s0)      # first use of the communicator: connection set-up
         torch.cuda.synchronize()
         dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         dev.bcast_state(0, stream=s0)
         e1.record()
@@ -510,8 +543,18 @@ def run_ours(args):
             Xd, zeta, sig, ymax, Kp, stream=stream, device_out=True, want_X=False)
         if world == 1:
             return acq, idx
-        out = dev.allgather_topk(acq, global_idx(idx), mean, std, None, Kp, d=0, stream=stream)
-        return out[0], out[1]
+        if comm is not None:
+            out = dev.allgather_topk(acq, global_idx(idx), mean, std, None, Kp, d=0,
+                                     stream=stream)
+            return out[0], out[1]
+        # torch.distributed exchange (the library's communicator is not up): all-gather of the
+        # per-GPU lists + exact top-K' of the union on the device
+        ga = torch.empty(world * Kp, dtype=torch.float64, device=dev_t)
+        gi = torch.empty(world * Kp, dtype=torch.int64, device=dev_t)
+        dist.all_gather_into_tensor(ga, acq.contiguous())
+        dist.all_gather_into_tensor(gi, global_idx(idx).contiguous())
+        order = torch.from_numpy(np.lexsort((gi.cpu().numpy(), -ga.cpu().numpy()))[:Kp]).to(dev_t)
+        return ga[order], gi[order]
 
     def barrier():
         if world > 1:
@@ -525,6 +568,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    PARTIAL["section"] = "warm-up / timed steps (device-resident)"
     for _ in range(args.warmup):
         step()
     dev.set_profiling(True)
@@ -542,6 +586,15 @@ def run_ours(args):
     tm = dev.timings(reset=True)
     dev.set_profiling(False)
     value = world * M * args.steps / (ms * 1e-3)
+    PARTIAL["line"] = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                       "dtype": "f64", "data": "synthetic",
+                       "config": {"workload": f"NORA ranked-pool scoring: predict mean+std + "
+                                              f"LogExp + top-{Kp}, N_train={N}, d={d}, RBF, {M} "
+                                              "candidates/GPU"},
+                       "gpu_launches": int(tm["launches"]), "clocks": clk}
+    PARTIAL["section"] = "e2e through NORA.multi_add"
 
     # ---- end to end: the acquisition step through the product API, PAGEABLE host candidates ----
     e2e, acquisition, nora_check = None, None, None
@@ -579,6 +632,8 @@ def run_ours(args):
         _, ms_pin, _ = timed(Xpin, max(1, min(args.steps, 2)))
         e2e["pinned"] = {"value": world * M / (ms_pin * 1e-3), "ms_per_step": ms_pin}
         del Xpin
+        PARTIAL["line"]["e2e"] = e2e
+        PARTIAL["section"] = "merged-pool checks"
         tmg = dict(nora.last_timing)
         acquisition = {"acquisition_step_ms": ms_page, "n_points": args.npoints,
                        "score_select_ms": tmg["score_s"] * 1e3,
@@ -602,6 +657,7 @@ def run_ours(args):
             "union_size": int(len(a)), "n_points_returned": int(len(X_pool))}
         del Xh
 
+    PARTIAL["section"] = "roofline / agreement"
     # ---- roofline of the dominant kernel (variance contraction) ----
     n_launch = max(tm["contract_launches"], 1.0)
     cands_per_launch = M * args.steps / n_launch
@@ -710,8 +766,9 @@ def run_ours(args):
         dist.all_gather_into_tensor(gi, global_idx(ref_idx[:Kp]).contiguous())
         ga, gi = ga.cpu().numpy(), gi.cpu().numpy()
         order = np.lexsort((gi, -ga))[:Kp]
-        merged_ok = bool(np.array_equal(np.asarray(top_idx), gi[order])
-                         and np.array_equal(np.asarray(top_acq), ga[order]))
+        to_np = lambda v: v.cpu().numpy() if hasattr(v, "cpu") else np.asarray(v)
+        merged_ok = bool(np.array_equal(to_np(top_idx), gi[order])
+                         and np.array_equal(to_np(top_acq), ga[order]))
         t = torch.tensor([float(local_ok), float(merged_ok)], dtype=torch.float64, device=dev_t)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         local_ok, merged_ok = bool(t[0] > 0), bool(t[1] > 0)
@@ -781,6 +838,9 @@ def run_ours(args):
                     cpu_baseline["acquisition_step"]["acquisition_step_ms_extrapolated"]
 
     # ---- secondary figures of the same path (not the headline metric) ----
+    PARTIAL["line"].update(roofline=roofline, agreement=agreement, cpu_baseline=cpu_baseline,
+                           acquisition=acquisition)
+    PARTIAL["section"] = "secondary figures"
     secondary = None
     if not args.no_secondary:     # every rank runs them; rank 0 reports the whole-job figures
         dev2 = DeviceGP(local)      # other models: must not disturb the regressor's device state
@@ -806,6 +866,8 @@ def run_ours(args):
             "tflops_algorithmic_per_gpu": flop_per_cand * M / (ms64 * 1e-3) * 1e-12,
             "frac_of_dgemm": flop_per_cand * M / (ms64 * 1e-3) * 1e-12 / peak,
             "what": "same step with the FP64 DMMA contraction (var_contract_kernel), 1 timed step"}
+        PARTIAL["line"]["secondary"] = dict(secondary)
+        PARTIAL["section"] = "secondary: 64-restart fit (config D)"
         try:
             secondary["fit"] = time_fit(world, rank, args.fit_restarts, dev_t,
                                         dist if world > 1 else None)
@@ -835,27 +897,50 @@ def run_ours(args):
                        "contraction_guard": contract_info,
                        "l2": "inputs (1.2 GB/GPU) and K* scratch (>500 MB) exceed the 126 MB L2",
                        "state_bcast_ms": t_bcast_ms,
-                       "exchange": "gpry_allgather_topk (ncclAllGather + device merge inside the "
-                                   "library)" if world > 1 else "none (1 GPU)"},
+                       "exchange": ("none (1 GPU)" if world == 1 else
+                                    "gpry_allgather_topk (ncclAllGather + device merge inside "
+                                    "the library)" if comm is not None else
+                                    "torch.distributed all_gather + merge (the library's own "
+                                    "communicator did not come up on this box)")},
             "e2e": e2e, "acquisition": acquisition,
             "gpu_launches": int(tm["launches"]), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "agreement": agreement, "clocks": clk,
             "secondary": secondary,
         }
-        print(json.dumps(line))
+        emit_line(line)
+    PARTIAL["section"] = "done"
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # The line is out.  Leave without running the NCCL destructors of two communicators in
+        # interpreter-exit order (a teardown that waits for a peer which is already gone would
+        # turn a finished run into a hung one): barrier, then a hard exit on every rank.
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stderr.flush()
+            os._exit(0)
     dev.close()
+
+
+def emit_line(line):
+    """The ONE JSON line, written to the real stdout at once (main() points fd 1 at stderr while
+    the run is on, so that library banners cannot reach stdout)."""
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT_FD if _REAL_STDOUT_FD is not None else 1
+    os.write(fd, data)
+    PARTIAL.pop("line", None)
 
 
 def main():
     args = parse_args()
     # Only the JSON line may reach stdout: libraries (NCCL prints its version banner there) are
     # pointed at stderr for the duration of the run.
+    global _REAL_STDOUT_FD
     sys.stdout.flush()
     saved_stdout = os.dup(1)
+    _REAL_STDOUT_FD = saved_stdout
     os.dup2(2, 1)
+    watchdog = start_watchdog()
     try:
         import io
         buf = io.StringIO()
@@ -868,6 +953,7 @@ def main():
         finally:
             sys.stdout = real_stdout
     finally:
+        watchdog.cancel()
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)

@@ -197,10 +197,16 @@ int comm_nccl_version() {
   return v;
 }
 
+// Two NCCL communicators must never have kernels in flight at the same time on a GPU (the host
+// process usually owns one of its own, e.g. PyTorch's): every collective of this file first
+// waits for everything queued on the device, and returns only when its own work is done.
+static void quiesce_device() { GPRY_CUDA(cudaDeviceSynchronize()); }
+
 void bcast_state(gpry_state* st, int root, cudaStream_t s) {
   ncclComm_t comm = comm_of(st);
   GPRY_CHECK_ARG(root >= 0 && root < st->comm_size, "bad root");
   GPRY_CUDA(cudaSetDevice(st->device));
+  quiesce_device();
   const bool am_root = st->comm_rank == root;
   if (am_root && !st->loaded)
     throw GpryError{GPRY_ERR_STATE, "bcast_state: the root has no model uploaded"};
@@ -265,6 +271,7 @@ void allgather_topk(gpry_state* st, int n_local, int Kp, int d, const double* ac
   GPRY_CHECK_ARG(d >= 0 && d <= MAX_DIM, "bad d");
   GPRY_CHECK_ARG(n_local == 0 || (acq && idx), "acq / idx missing");
   GPRY_CUDA(cudaSetDevice(st->device));
+  quiesce_device();
   const int W = st->comm_size, R = 4 + d;
   const size_t rec_local = (size_t)Kp * R, n_union = (size_t)W * Kp;
   st->cm_send.reserve(rec_local + (size_t)Kp * (3 + d) + Kp);

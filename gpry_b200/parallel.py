@@ -205,20 +205,64 @@ def allgather_survivors(acq, idx, mean, std, X):
 _device_comm = {}
 
 
-def device_comm(device=None):
+def device_comm(device=None, timeout=90.0):
     """The process-wide ``DeviceGP`` of this rank's GPU with the library's own NCCL communicator
     over the whole process group (created on first use: rank 0 makes the 128-byte id, it travels
-    through ``bcast``), or None when the ranks do not each own a GPU (gloo / serial runs)."""
+    through ``bcast``), or None when the ranks do not each own a GPU (gloo / serial runs), when
+    ``GPRY_B200_LIB_COMM=0``, or when the communicator could not be brought up.
+
+    The bring-up (``ncclCommInitRank`` + one tiny all-gather through the new communicator as a
+    self-test) runs in a helper thread with a time limit, and the ranks then agree on the outcome:
+    a second NCCL communicator next to the host framework's is the one step of this path that
+    depends on the fabric configuration of the box, and a stuck bootstrap must not take the job
+    with it -- the exchange steps then go through ``torch.distributed`` (same NCCL, the
+    framework's communicator)."""
+    import os
+    import threading
+    import warnings
     if not (_on() and multiple_processes() and dist.get_backend() == "nccl"):
+        return None
+    # GPRY_B200_LIB_COMM: "1" always try, "0" never, unset: on boxes of up to 2 GPUs -- the
+    # configuration this was validated on (tests/test_gpu_multi.py, profiles/r02_bench_n2.json);
+    # the round-2 attempt on 8 GPUs did not complete and could not be diagnosed before the GPU
+    # budget ran out, so larger jobs use torch.distributed's communicator unless asked to.
+    want = os.environ.get("GPRY_B200_LIB_COMM")
+    if want == "0" or (want is None and size() > 2):
         return None
     from .device import workspace
     device = torch.cuda.current_device() if device is None else device
-    if device not in _device_comm:
-        ws = workspace(device)
-        uid = bcast(ws.comm_unique_id() if is_main_process() else None)
-        ws.comm_init(uid, rank(), size())
-        _device_comm[device] = ws
-    return _device_comm[device]
+    if device in _device_comm:
+        return _device_comm[device]
+    ws = workspace(device)
+    uid = bcast(ws.comm_unique_id() if is_main_process() else None)
+    torch.cuda.synchronize()
+    outcome = {}
+
+    def bring_up():
+        try:
+            ws.comm_init(uid, rank(), size())
+            me = float(rank())
+            got = ws.allgather_topk(np.array([me]), np.array([rank()], dtype=np.int64),
+                                    np.array([me]), np.array([me]), np.array([[me]]), 1)
+            outcome["ok"] = bool(len(got[0]) == 1 and got[0][0] == size() - 1
+                                 and got[1][0] == size() - 1)
+        except Exception as excpt:          # reported below, on every rank
+            outcome["error"] = repr(excpt)
+
+    t = threading.Thread(target=bring_up, daemon=True)
+    t.start()
+    t.join(timeout)
+    ok = bool(outcome.get("ok", False))
+    ok_everywhere = all(allgather(ok))
+    if not ok_everywhere:
+        if is_main_process():
+            warnings.warn("gpry_b200: the library's NCCL communicator did not come up "
+                          f"({outcome.get('error', 'timeout' if t.is_alive() else 'self-test failed')}); "
+                          "exchange steps use torch.distributed collectives")
+        _device_comm[device] = None
+        return None
+    _device_comm[device] = ws
+    return ws
 
 
 def merge_survivors(acq, idx, mean, std, X, Kp):
@@ -284,6 +328,13 @@ def fit_gpr_parallel(gpr, new_X, new_y, n_restarts=None, hyperparameter_bounds=N
         else:   # no run assigned: still add the points (kept-constant hyper-parameters)
             gpr.append_to_data(new_X, new_y, fit_classifier=True, fit_gpr=False)
             lml = -np.inf
+    except np.linalg.LinAlgError:
+        # This rank's best restart ended where the kernel matrix is not positive definite.  It
+        # must still take part in the exchange below (a rank that raised here would leave the
+        # others waiting in the all-gather for ever): it reports -inf and adopts the winner.
+        if not multiple_processes():
+            raise
+        lml = -np.inf
     finally:
         gpr.random_state = seed
     theta = gpr.kernel_.theta
@@ -299,4 +350,7 @@ def fit_gpr_parallel(gpr, new_X, new_y, n_restarts=None, hyperparameter_bounds=N
         gpr._update_model()
         gpr.log_marginal_likelihood_value_ = best_lml
         gpr._fitted = True
+    elif multiple_processes():
+        raise np.linalg.LinAlgError("hyper-parameter fit: no rank found a positive definite "
+                                    "kernel matrix")
     return best_rank
