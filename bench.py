@@ -39,8 +39,8 @@ UNIT = "candidates/s"
 FP64_DGEMM_FALLBACK_TFLOPS = 35.4   # cublasDgemm 8192^3 on this pool (profiles/r01_fp64_peaks.txt)
 PROFILE_INT8 = "r02_oz_contract_ncu.json"      # ncu --set full capture of the INT8 contraction
 PROFILE_FP64 = "r01_contract_ncu.json"         # ... and of the FP64 (DMMA) contraction
-KERNEL_INT8 = ("oz2_contract_kernel (INT8 Ozaki split, two passes of 128x128x32 tcgen05.mma "
-               "kind::i8, TMEM)")
+KERNEL_INT8 = ("oz2_contract_kernel (INT8 Ozaki split, two passes over the digit groups, "
+               "tcgen05.mma kind::i8 128x256x32 per pair of V digits, int32 accumulators in TMEM)")
 
 
 # ------------------------------------------------------------------------------------------
@@ -60,6 +60,8 @@ def _watchdog_fire():
         faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
     except Exception:
         pass
+    if PARTIAL.get("emitted"):          # the line is out: only the teardown is stuck
+        os._exit(0)
     if int(os.environ.get("RANK", "0")) == 0 and "line" in PARTIAL:
         line = dict(PARTIAL["line"])
         line["incomplete"] = f"watchdog after {WATCHDOG_S:.0f} s in section '{PARTIAL['section']}'"
@@ -913,6 +915,11 @@ def run_ours(args):
         # The line is out.  Leave without running the NCCL destructors of two communicators in
         # interpreter-exit order (a teardown that waits for a peer which is already gone would
         # turn a finished run into a hung one): barrier, then a hard exit on every rank.
+        import threading
+        PARTIAL["emitted"] = True
+        last = threading.Timer(60.0, lambda: os._exit(0))      # a peer that is gone must not hold us
+        last.daemon = True
+        last.start()
         try:
             dist.barrier()
             torch.cuda.synchronize()
@@ -928,7 +935,7 @@ def emit_line(line):
     data = (json.dumps(line) + "\n").encode()
     fd = _REAL_STDOUT_FD if _REAL_STDOUT_FD is not None else 1
     os.write(fd, data)
-    PARTIAL.pop("line", None)
+    PARTIAL["emitted"] = True
 
 
 def main():
