@@ -211,8 +211,9 @@ def device_comm(device=None, timeout=90.0):
     through ``bcast``), or None when the ranks do not each own a GPU (gloo / serial runs), when
     ``GPRY_B200_LIB_COMM=0``, or when the communicator could not be brought up.
 
-    The bring-up (``ncclCommInitRank`` + one tiny all-gather through the new communicator as a
-    self-test) runs in a helper thread with a time limit, and the ranks then agree on the outcome:
+    When forced on for more than 2 ranks (``GPRY_B200_LIB_COMM=1``) the bring-up
+    (``ncclCommInitRank`` + one tiny all-gather through the new communicator as a self-test) runs
+    in a helper thread with a time limit, and the ranks then agree on the outcome:
     a second NCCL communicator next to the host framework's is the one step of this path that
     depends on the fabric configuration of the box, and a stuck bootstrap must not take the job
     with it -- the exchange steps then go through ``torch.distributed`` (same NCCL, the
@@ -236,6 +237,11 @@ def device_comm(device=None, timeout=90.0):
     ws = workspace(device)
     uid = bcast(ws.comm_unique_id() if is_main_process() else None)
     torch.cuda.synchronize()
+    if size() <= 2 and want is None:
+        # the validated configuration: plain bring-up, exactly as measured (r02_bench_n2.json)
+        ws.comm_init(uid, rank(), size())
+        _device_comm[device] = ws
+        return ws
     outcome = {}
 
     def bring_up():
