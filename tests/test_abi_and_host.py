@@ -271,3 +271,27 @@ def test_build_entry_point():
     ge = importlib.import_module("__graft_entry__")
     ge.build()
     assert os.path.exists(os.path.join(ROOT, "gpry_b200", "libgpry_b200.so"))
+
+
+def test_bench_watchdog_prints_what_was_measured():
+    """A multi-GPU bench run that stops making progress must not hang its caller: the watchdog
+    dumps the stacks, rank 0 prints the line with what has been measured so far (marked
+    "incomplete"), and the process exits; once the line is out, only exit."""
+    import json
+    import subprocess
+    import sys
+    code = (
+        "import sys, os\n"
+        "sys.argv = ['bench.py']\n"
+        "import bench\n"
+        "bench._REAL_STDOUT_FD = 1\n"
+        "bench.PARTIAL['line'] = {'metric': bench.METRIC, 'value': 2.0, 'n_gpus': 4}\n"
+        "bench.PARTIAL['section'] = 'secondary figures'\n"
+        "bench._watchdog_fire()\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert out.returncode == 0
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["value"] == 2.0 and "secondary figures" in line["incomplete"]
+    code2 = code.replace("bench._watchdog_fire()", "bench.emit_line({'a': 1}); bench._watchdog_fire()")
+    out = subprocess.run([sys.executable, "-c", code2], cwd=ROOT, capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == '{"a": 1}'
