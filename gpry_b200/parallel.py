@@ -121,7 +121,11 @@ def step_split(values, root=0):
     """mpi.py:105-115: broadcast from rank 0, keep ``values[RANK::SIZE]``."""
     if not multiple_processes():
         return values
-    values = bcast(values, root=root)
+    # float64 arrays travel as tensors (no pickling: an MC sample can be GBs), anything else as
+    # an object like in the reference
+    as_array = bcast(isinstance(values, np.ndarray) and values.dtype == np.float64
+                     if rank() == root else None, root=root)
+    values = bcast_array(values, root=root) if as_array else bcast(values, root=root)
     return values[rank()::size()]
 
 
