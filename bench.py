@@ -903,7 +903,9 @@ def run_ours(args):
                                     "gpry_allgather_topk (ncclAllGather + device merge inside "
                                     "the library)" if comm is not None else
                                     "torch.distributed all_gather + merge (the library's own "
-                                    "communicator did not come up on this box)")},
+                                    "NCCL communicator is brought up by default only on the "
+                                    "configuration it was validated on, <= 2 ranks: "
+                                    "profiles/r02_bench_n2.json; GPRY_B200_LIB_COMM=1 forces it)")},
             "e2e": e2e, "acquisition": acquisition,
             "gpu_launches": int(tm["launches"]), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "agreement": agreement, "clocks": clk,
