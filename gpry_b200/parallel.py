@@ -243,9 +243,15 @@ def device_comm(device=None, timeout=90.0):
     torch.cuda.synchronize()
     if size() <= 2 and want is None:
         # the validated configuration: plain bring-up, exactly as measured (r02_bench_n2.json)
-        ws.comm_init(uid, rank(), size())
-        _device_comm[device] = ws
-        return ws
+        try:
+            ws.comm_init(uid, rank(), size())
+            ok = True
+        except Exception as excpt:      # e.g. no NCCL library to bind: same decision on all ranks
+            ok = False
+            warnings.warn(f"gpry_b200: NCCL communicator of the library not available ({excpt}); "
+                          "exchange steps use torch.distributed collectives")
+        _device_comm[device] = ws if all(allgather(ok)) else None
+        return _device_comm[device]
     outcome = {}
 
     def bring_up():
