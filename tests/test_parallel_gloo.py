@@ -215,6 +215,38 @@ def _worker(rank, world, port, out_dir):
     assert np.array_equal(preds[0], preds[1])
     # the reference's own fit of this case (golden): the parallel fit is at least as good
     assert lmls[0] >= float(z["lml_opt"]) - 1e-6 * abs(float(z["lml_opt"]))
+    # same integer seed on every rank: the ranks must still draw DIFFERENT restart points
+    # (children of one SeedSequence, mpi.py:31-50), and the seed is restored afterwards
+    fit2 = gpr_mod.GaussianProcessRegressor(
+        kernel="RBF", bounds=z["bounds"], noise_level=1e-2, n_restarts_optimizer=4,
+        preprocessing_X=Normalize_bounds(z["bounds"]), preprocessing_y=Normalize_y(),
+        account_for_inf=None, random_state=7, verbose=0)
+    seen = {}
+    orig = fit2._lockstep_optimization
+    fit2._lockstep_optimization = lambda starts, b: (seen.setdefault("starts", np.array(starts)),
+                                                     orig(starts, b))[1]
+    parallel.fit_gpr_parallel(fit2, z["X_train"], z["y_train"])
+    starts = parallel.allgather(seen["starts"])
+    assert not np.array_equal(starts[0], starts[1]) and fit2.random_state == 7
+    # a rank whose own fit ends at a non-positive-definite matrix still takes part in the
+    # exchange and adopts the winner (instead of leaving the others in the all-gather)
+    fit3 = gpr_mod.GaussianProcessRegressor(
+        kernel="RBF", bounds=z["bounds"], noise_level=1e-2, n_restarts_optimizer=4,
+        preprocessing_X=Normalize_bounds(z["bounds"]), preprocessing_y=Normalize_y(),
+        account_for_inf=None, random_state=11, verbose=0)
+    if rank == 1:
+        real_fit = fit3.fit_gpr_hyperparameters
+
+        def failing_fit(**kw):
+            real_fit(**kw)
+            raise np.linalg.LinAlgError("not positive definite (simulated)")
+        fit3.fit_gpr_hyperparameters = failing_fit
+    winner = parallel.fit_gpr_parallel(fit3, z["X_train"], z["y_train"])
+    assert winner == 0
+    th3 = parallel.allgather(np.array(fit3.kernel_.theta))
+    assert np.array_equal(th3[0], th3[1]) and fit3.fitted
+    p3 = parallel.allgather(fit3.predict(z["Xc"]))
+    assert np.array_equal(p3[0], p3[1])
     dist.barrier()
     dist.destroy_process_group()
 
