@@ -49,7 +49,7 @@ KERNEL_INT8 = ("oz2_contract_kernel (INT8 Ozaki split, two passes over the digit
 # prints the line with what has been measured so far ("incomplete": the section it was in), and
 # the process exits.
 # ------------------------------------------------------------------------------------------
-WATCHDOG_S = float(os.environ.get("GPRY_B200_BENCH_WATCHDOG_S", "900"))
+WATCHDOG_S = float(os.environ.get("GPRY_B200_BENCH_WATCHDOG_S", "420"))
 PARTIAL = {"section": "start"}
 _REAL_STDOUT_FD = None
 
