@@ -504,8 +504,9 @@ def run_ours(args):
     if comm is not None:
         dev = gpr._device_state() if rank == 0 else DeviceGP(local)
         dev.comm_share(comm)
+        # (one call, the sequence validated on hardware: the time includes the communicator's
+        # connection set-up on first use; 32 MB over NVLink are ~0.1 ms of it)
         s0 = torch.cuda.current_stream()
-        dev.bcast_state(0, stream=s0)      # first use of the communicator: connection set-up
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
@@ -899,6 +900,8 @@ def run_ours(args):
                        "contraction_guard": contract_info,
                        "l2": "inputs (1.2 GB/GPU) and K* scratch (>500 MB) exceed the 126 MB L2",
                        "state_bcast_ms": t_bcast_ms,
+                       "state_bcast_note": "gpry_bcast_state, first use of the library's "
+                                           "communicator (connection set-up included)",
                        "exchange": ("none (1 GPU)" if world == 1 else
                                     "gpry_allgather_topk (ncclAllGather + device merge inside "
                                     "the library)" if comm is not None else
